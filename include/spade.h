@@ -1,0 +1,145 @@
+/*
+ * libspade_b200 - C ABI of the B200 engine for pySpade's hypergeometric
+ * differential-expression hot path.
+ *
+ * The reference (Hon-lab/pySpade v0.1.7) is pure Python and has no FFI; the seam
+ * this library sits behind is the pair of functions
+ *     perform_DE(sgrna_idx, input_array, idx, num_processes, down, up, fc, cpm)
+ *         pySpade/utils.py:296-317
+ *     perform_DE_NC(sgrna_idx, NC_idx, input_array, idx, num_processes, ...)
+ *         pySpade/utils.py:319-341
+ * called once per perturbation region by DEobs.py:137,197 and once per random
+ * draw by DErand.py:143,207.  Each entry point below names the reference lines
+ * it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status, 0 = SPADE_OK; nothing throws across
+ *     the ABI; spade_last_error() gives the message of the last failure;
+ *   - input buffers are borrowed for the duration of the call only;
+ *   - outputs are caller-allocated; "location" arguments say whether a pointer
+ *     is host (SPADE_HOST) or device (SPADE_DEVICE) memory;
+ *   - one engine per GPU; an engine is not thread-safe; engines are independent;
+ *   - no CPU fallback: without a CUDA device every call fails with SPADE_ERR_CUDA.
+ *
+ * Vocabulary: G genes, C cells, a "set" is the list of member cells of one
+ * perturbation region (DEobs) or one random draw (DErand); a "test" is one
+ * (gene, set) pair.
+ */
+#ifndef SPADE_B200_H
+#define SPADE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPADE_OK 0
+#define SPADE_ERR_ARG 1      /* bad argument (null pointer, index out of range, ...) */
+#define SPADE_ERR_CUDA 2     /* CUDA runtime failure, no device, out of memory */
+#define SPADE_ERR_STATE 3    /* call not valid in the engine's current state */
+
+#define SPADE_HOST 0
+#define SPADE_DEVICE 1
+
+#define SPADE_ABI_VERSION 1
+
+typedef struct spade_engine spade_engine;
+
+/* ABI version of the loaded library (compare with SPADE_ABI_VERSION). */
+int spade_abi_version(void);
+
+/* Message of the last failure on this engine (or of the last failed
+ * spade_create* when engine is NULL).  Never NULL; valid until the next call. */
+const char *spade_last_error(const spade_engine *engine);
+
+/*
+ * Stage a genes x cells matrix of already-normalised float64 expression values
+ * (CSR: indptr[G+1], indices[nnz] = cell index, values[nnz]) on GPU `device`.
+ * Replaces what the reference redoes on every call: input_array.tocsr() and the
+ * per-row pickling (utils.py:303-307, 325-331), np.median over the dense row and
+ * the low-set selection (utils.py:199-200).  One-time work per matrix:
+ * per-gene median cutoff, n_g = #{cells <= median}, per-entry "above cutoff"
+ * flags, row sums, and the cell-major (CSC) copy the batched test walks.
+ * Column indices inside a row must be unique; they need not be sorted.
+ */
+int spade_create(int device, int64_t G, int64_t C, const int64_t *indptr, const int32_t *indices,
+                 const double *values, int location, spade_engine **engine_out);
+
+/*
+ * Same, from raw integer UMI counts: runs the reference's CPM normalisation
+ * (cpm_normalization, utils.py:150-155; value = fl(fl(x*1e6) * fl(1/colsum)),
+ * bit-identical to the reference) on the device first.
+ */
+int spade_create_from_counts(int device, int64_t G, int64_t C, const int64_t *indptr,
+                             const int32_t *indices, const int32_t *counts, int location,
+                             spade_engine **engine_out);
+
+void spade_destroy(spade_engine *engine);
+
+/*
+ * Choose the background.  n_nc == 0: complement background (hypergeo_test_sparse,
+ * utils.py:194-215).  n_nc > 0: negative-control background
+ * (hypergeo_test_NC_sparse, utils.py:248-266): median over the NC cells only,
+ * low set over all cells, fold-change denominator = mean over the NC cells.
+ * nc_idx is a host array of unique cell indices.  Re-stages cutoffs and flags.
+ */
+int spade_set_background(spade_engine *engine, const int32_t *nc_idx, int64_t n_nc);
+
+/* Matrix facts: G, C, stored non-zeros, and the fixed-point shift of the sums. */
+int spade_dims(const spade_engine *engine, int64_t *G, int64_t *C, int64_t *nnz, int32_t *fix_shift);
+
+/* Per-gene cutoffs for integer parity checks (host outputs, either may be NULL):
+ * median[G] (float64) and n[G] = #{cells : x <= median} (int32). */
+int spade_gene_cutoffs(spade_engine *engine, double *median, int32_t *n);
+
+/* Copy the staged CPM values back in the caller's CSR order (host output,
+ * float64[nnz]); parity check of spade_create_from_counts against utils.py:150-155. */
+int spade_cpm_values(spade_engine *engine, double *values);
+
+/*
+ * The batched test: every gene against S cell sets.  Replaces S calls of
+ * perform_DE / perform_DE_NC (utils.py:296-341), i.e. G*S calls of
+ * hypergeo_test[_NC]_sparse (utils.py:194-215 / 248-266).
+ *
+ *   members   int32[offsets[S]]  concatenated member cell indices (no duplicates
+ *                                inside a set), host or device per members_location
+ *   offsets   int64[S+1]         HOST array, offsets[0] == 0, non-decreasing
+ *   up, down, fc, cpm            float64[S*G], row-major [set][gene]; any may be NULL
+ *                                up   = hypergeom.logcdf(k, M, n, N)   (utils.py:212)
+ *                                down = hypergeom.logsf (k, M, n, N)   (utils.py:213)
+ *                                both nan when any of k, M, n, N is 0
+ *                                fc   = (mean_set+.01)/(mean_background+.01) (utils.py:207 / :258)
+ *                                cpm  = mean over the set's cells     (utils.py:208 / :259)
+ *   k         int32[S*G]         optional: |{cells <= cutoff} ∩ set|  (utils.py:203,211)
+ *   out_location                 SPADE_HOST or SPADE_DEVICE for all five outputs
+ *   stream                       cudaStream_t (as void*) the work is ordered on; NULL =
+ *                                the legacy default stream.  With device outputs the call
+ *                                returns without synchronising.
+ */
+int spade_run(spade_engine *engine, const int32_t *members, int members_location,
+              const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
+              int32_t *k, int out_location, void *stream);
+
+/* Kernel-time accounting (CUDA events on the launch stream, accumulated since
+ * the last reset).  Synchronises.  launches = kernels launched by spade_run. */
+int spade_timing(spade_engine *engine, double *accumulate_ms, double *finalize_ms, int64_t *launches,
+                 int reset);
+
+/*
+ * K3 in isolation (parity probe): logcdf / logsf of scipy.stats.hypergeom for `count`
+ * tuples (k, M, n, N) given as host int64 arrays, results to host float64 arrays.  Plain
+ * scipy semantics (support clamps, nan for invalid shapes); the reference's
+ * all([k, M, n, N]) guard of utils.py:212-213 is NOT applied here.
+ */
+int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_t *n,
+                    const int64_t *N, int64_t count, double *logcdf, double *logsf);
+
+/* Page-locked host memory for result tables (fast device->host copies). */
+int spade_host_alloc(void **ptr, int64_t bytes);
+int spade_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPADE_B200_H */

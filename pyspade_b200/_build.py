@@ -1,0 +1,41 @@
+"""Build ``libspade_b200.so`` in-tree with nvcc for sm_100a.
+
+The shared library is the product's only native artefact; it is git-ignored
+(``*.so``) but travels to the GPU box with the ``gpurun`` snapshot.
+"""
+import os
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+SRC = os.path.join(PKG, "csrc", "spade_kernels.cu")
+HDR = os.path.join(ROOT, "include", "spade.h")
+OUT = os.path.join(PKG, "libspade_b200.so")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-shared", "-Xcompiler", "-fPIC",
+    "-I", os.path.join(ROOT, "include"),
+]
+
+
+def needs_build() -> bool:
+    if not os.path.isfile(OUT):
+        return True
+    newest = max(os.path.getmtime(p) for p in (SRC, HDR))
+    return os.path.getmtime(OUT) < newest
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,273 @@
+"""Python face of one staged matrix on one GPU (``spade_engine`` of ``include/spade.h``).
+
+``Engine.run`` is the batched form of the reference's ``perform_DE`` /
+``perform_DE_NC`` (``/root/reference/pySpade/utils.py:296-341``): every gene
+against S cell sets in one call.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+TABLES = ("up", "down", "fc", "cpm")
+
+
+class SpadeError(RuntimeError):
+    pass
+
+
+def _ptr(arr):
+    if arr is None:
+        return None
+    return ctypes.c_void_p(arr.ctypes.data)
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from ``spade_host_alloc``."""
+
+    def __init__(self, shape, dtype):
+        lib = _lib.load()
+        self._lib = lib
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = ctypes.c_void_p()
+        rc = lib.spade_host_alloc(ctypes.byref(p), nbytes)
+        if rc != _lib.SPADE_OK:
+            raise SpadeError(lib.spade_last_error(None).decode())
+        self._p = p
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            self._lib.spade_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One genes x cells matrix staged in the HBM of one GPU."""
+
+    def __init__(self, handle, device):
+        self._lib = _lib.load()
+        self._h = handle
+        self.device = device
+        G, C, nnz = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        f = ctypes.c_int32()
+        self._check(self._lib.spade_dims(self._h, ctypes.byref(G), ctypes.byref(C),
+                                         ctypes.byref(nnz), ctypes.byref(f)))
+        self.G, self.C, self.nnz, self.fix_shift = G.value, C.value, nnz.value, f.value
+        self.n_nc = 0
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def _csr_parts(matrix, value_dtype):
+        m = sp.csr_matrix(matrix)
+        if not m.has_canonical_format:
+            m = m.copy()
+            m.sum_duplicates()
+        indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        data = np.ascontiguousarray(m.data, dtype=value_dtype)
+        return m.shape, indptr, indices, data
+
+    @classmethod
+    def _create(cls, fn_name, device, G, C, indptr_p, indices_p, data_p, location):
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = getattr(lib, fn_name)(int(device), int(G), int(C), indptr_p, indices_p, data_p,
+                                   int(location), ctypes.byref(h))
+        if rc != _lib.SPADE_OK:
+            raise SpadeError(f"{fn_name} failed ({rc}): {lib.spade_last_error(None).decode()}")
+        return cls(h, device)
+
+    @classmethod
+    def from_cpm(cls, matrix, device=0):
+        """Stage already-normalised float64 values (the ``input_array`` of
+        ``perform_DE``, utils.py:296)."""
+        (G, C), indptr, indices, data = cls._csr_parts(matrix, np.float64)
+        return cls._create("spade_create", device, G, C, _ptr(indptr), _ptr(indices), _ptr(data),
+                           _lib.SPADE_HOST)
+
+    @classmethod
+    def from_counts(cls, counts, device=0):
+        """Stage raw integer counts; CPM normalisation (utils.py:150-155) runs on the GPU."""
+        (G, C), indptr, indices, data = cls._csr_parts(counts, np.int32)
+        return cls._create("spade_create_from_counts", device, G, C, _ptr(indptr), _ptr(indices),
+                           _ptr(data), _lib.SPADE_HOST)
+
+    @classmethod
+    def from_device_csr(cls, G, C, indptr, indices, data, device=0):
+        """CSR already resident on the GPU as torch tensors (int64 / int32 / float64 or
+        int32 counts)."""
+        import torch
+
+        assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
+        fn = "spade_create_from_counts" if data.dtype == torch.int32 else "spade_create"
+        if fn == "spade_create":
+            assert data.dtype == torch.float64
+        torch.cuda.synchronize(device)
+        return cls._create(fn, device, G, C, ctypes.c_void_p(indptr.data_ptr()),
+                           ctypes.c_void_p(indices.data_ptr()), ctypes.c_void_p(data.data_ptr()),
+                           _lib.SPADE_DEVICE)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != _lib.SPADE_OK:
+            raise SpadeError(f"libspade_b200 error {rc}: "
+                             f"{self._lib.spade_last_error(self._h).decode()}")
+
+    def close(self):
+        if self._h is not None:
+            self._lib.spade_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ background
+    def set_background(self, nc_idx=None):
+        """``None`` / empty: complement background (utils.py:194-215); otherwise the
+        negative-control cells of ``hypergeo_test_NC_sparse`` (utils.py:248-266)."""
+        if nc_idx is None or len(nc_idx) == 0:
+            self._check(self._lib.spade_set_background(self._h, None, 0))
+            self.n_nc = 0
+            return
+        nc = np.ascontiguousarray(np.asarray(nc_idx), dtype=np.int32)
+        self._check(self._lib.spade_set_background(self._h, _ptr(nc), nc.shape[0]))
+        self.n_nc = int(nc.shape[0])
+
+    # ------------------------------------------------------------------ parity probes
+    def gene_cutoffs(self):
+        med = np.empty(self.G, dtype=np.float64)
+        n = np.empty(self.G, dtype=np.int32)
+        self._check(self._lib.spade_gene_cutoffs(self._h, _ptr(med), _ptr(n)))
+        return med, n
+
+    def cpm_values(self):
+        vals = np.empty(self.nnz, dtype=np.float64)
+        self._check(self._lib.spade_cpm_values(self._h, _ptr(vals)))
+        return vals
+
+    # ------------------------------------------------------------------ the batched test
+    @staticmethod
+    def pack_sets(sets):
+        offsets = np.zeros(len(sets) + 1, dtype=np.int64)
+        if len(sets):
+            offsets[1:] = np.cumsum([len(s) for s in sets])
+        if offsets[-1] > 0:
+            members = np.concatenate([np.asarray(s, dtype=np.int64).ravel() for s in sets])
+        else:
+            members = np.zeros(0, dtype=np.int64)
+        return members, offsets
+
+    def _validate_members(self, members, offsets):
+        if members.shape[0] == 0:
+            return
+        if members.min() < 0 or members.max() >= self.C:
+            raise IndexError("cell index out of range in a cell set")
+        # N counts duplicates while k de-duplicates in the reference (utils.py:203,211);
+        # draws and set()-derived region lists never hold duplicates, so they are refused.
+        set_id = np.repeat(np.arange(offsets.shape[0] - 1, dtype=np.int64), np.diff(offsets))
+        key = set_id * np.int64(self.C) + members
+        if np.unique(key).shape[0] != key.shape[0]:
+            raise ValueError("duplicate cell index inside a cell set")
+
+    def run(self, sets=None, members=None, offsets=None, want_k=False, out=None, validate=True,
+            tables=TABLES):
+        """Test every gene against each cell set.
+
+        ``sets``: list of index arrays, or pass packed ``members`` + ``offsets``.
+        Returns a dict of float64 arrays ``[S, G]`` (``up, down, fc, cpm``; plus int32 ``k``
+        when ``want_k``).  ``out`` may hold preallocated arrays (e.g. pinned) to fill."""
+        if sets is not None:
+            members, offsets = self.pack_sets(sets)
+        members = np.asarray(members)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        S = offsets.shape[0] - 1
+        if validate:
+            self._validate_members(members.astype(np.int64, copy=False), offsets)
+        members = np.ascontiguousarray(members, dtype=np.int32)
+        res = {}
+        for name in tables:
+            if out is not None and name in out:
+                arr = out[name]
+                assert arr.dtype == np.float64 and arr.shape == (S, self.G) and arr.flags.c_contiguous
+            else:
+                arr = np.empty((S, self.G), dtype=np.float64)
+            res[name] = arr
+        if want_k:
+            res["k"] = (out["k"] if out is not None and "k" in out
+                        else np.empty((S, self.G), dtype=np.int32))
+        self._check(self._lib.spade_run(
+            self._h, _ptr(members), _lib.SPADE_HOST, _ptr(offsets), S,
+            _ptr(res.get("up")), _ptr(res.get("down")), _ptr(res.get("fc")), _ptr(res.get("cpm")),
+            _ptr(res.get("k")), _lib.SPADE_HOST, None))
+        return res
+
+    def run_device(self, members, offsets_host, out, k=None, stream=None):
+        """Device-resident form: ``members`` int32 torch tensor on this GPU,
+        ``offsets_host`` int64 numpy, ``out`` dict of float64 torch tensors ``[S, G]``.
+        Ordered on ``stream`` (a ``torch.cuda.Stream``; default: torch's current
+        stream); returns without synchronising."""
+        import torch
+
+        offsets = np.ascontiguousarray(offsets_host, dtype=np.int64)
+        S = offsets.shape[0] - 1
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+
+        def dp(t):
+            if t is None:
+                return None
+            assert t.is_cuda and t.is_contiguous()
+            return ctypes.c_void_p(t.data_ptr())
+
+        for name in TABLES:
+            t = out.get(name)
+            if t is not None:
+                assert t.dtype == torch.float64 and tuple(t.shape) == (S, self.G)
+        assert members.dtype == torch.int32
+        self._check(self._lib.spade_run(
+            self._h, dp(members), _lib.SPADE_DEVICE, _ptr(offsets), S,
+            dp(out.get("up")), dp(out.get("down")), dp(out.get("fc")), dp(out.get("cpm")),
+            dp(k), _lib.SPADE_DEVICE, ctypes.c_void_p(stream.cuda_stream)))
+
+    def timing(self, reset=False):
+        a, f, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        self._check(self._lib.spade_timing(self._h, ctypes.byref(a), ctypes.byref(f),
+                                           ctypes.byref(n), 1 if reset else 0))
+        return dict(accumulate_ms=a.value, finalize_ms=f.value, launches=n.value)
+
+
+def hypergeom_logcdf_logsf(k, M, n, N, device=0):
+    """K3 in isolation on the GPU (``spade_hypergeom``): scipy semantics, no nan guard."""
+    lib = _lib.load()
+    shape = np.broadcast_shapes(np.shape(k), np.shape(M), np.shape(n), np.shape(N))
+    arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.int64), shape)).ravel()
+            for a in (k, M, n, N)]
+    count = arrs[0].shape[0]
+    lc = np.empty(count, dtype=np.float64)
+    ls = np.empty(count, dtype=np.float64)
+    rc = lib.spade_hypergeom(int(device), _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), _ptr(arrs[3]),
+                             count, _ptr(lc), _ptr(ls))
+    if rc != _lib.SPADE_OK:
+        raise SpadeError(f"spade_hypergeom failed ({rc}): {lib.spade_last_error(None).decode()}")
+    return lc.reshape(shape), ls.reshape(shape)

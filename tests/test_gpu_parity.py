@@ -1,0 +1,201 @@
+"""GPU tier: the CUDA path (through the C ABI) against the oracle and the golden
+fixtures.  Integers (k, n) bit-exact; log p-values, fold changes and mean CPM within
+1e-6 relative (north_star); nan / -inf / 0.0 positions identical."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import LOGP_RTOL, assert_tables_close, max_rel_err, parse_float, sets_from_packed
+from oracle import c_oracle, de_port
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(*a, **k):
+    from pyspade_b200.engine import Engine
+    return Engine
+
+
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_cpm_on_device_bit_identical(small_case, tag):
+    from pyspade_b200.engine import Engine
+    z = small_case
+    counts = sp.csr_matrix(z[f"{tag}_counts"])
+    counts.sort_indices()
+    with Engine.from_counts(counts) as eng:
+        assert np.array_equal(eng.cpm_values(), z[f"{tag}_cpm_data"])     # utils.py:150-155, bit-exact
+
+
+@pytest.mark.parametrize("tag", ["odd", "even"])
+@pytest.mark.parametrize("mode", ["complement", "nc"])
+@pytest.mark.parametrize("source", ["counts", "cpm"])
+def test_small_case_vs_reference(small_case, tag, mode, source):
+    from pyspade_b200.engine import Engine
+    z = small_case
+    counts = sp.csr_matrix(z[f"{tag}_counts"])
+    if source == "counts":
+        eng = Engine.from_counts(counts)
+    else:
+        eng = Engine.from_cpm(de_port.cpm_normalization_port(counts))
+    sets = sets_from_packed(z[f"{tag}_set_members"], z[f"{tag}_set_offsets"])
+    nc = z[f"{tag}_nc_idx"] if mode == "nc" else None
+    with eng:
+        eng.set_background(nc)
+        got = eng.run(sets, want_k=True)
+        med, n = eng.gene_cutoffs()
+    X = de_port.cpm_normalization_port(counts)
+    ora = de_port.de_tables(X, sets, nc)
+    assert np.array_equal(med, ora["median"])          # float64 cutoffs, bit-exact
+    assert np.array_equal(n, ora["n"])                 # integers, bit-exact
+    assert np.array_equal(got["k"], ora["k"])
+    want = {name: z[f"{tag}_{mode}_{name}"] for name in ("up", "down", "fc", "cpm")}
+    assert_tables_close(got, want)                     # against the reference's own output
+    assert_tables_close(got, ora)
+
+
+def test_kat_genes(kat):
+    from pyspade_b200.engine import Engine
+    C = kat["C"]
+    A = np.zeros(C); A[:600] = np.arange(600) + 1.0
+    B = np.zeros(C); B[::7] = 3.0; B[::35] = 9.0
+    Z = np.zeros(C)
+    X = sp.csr_matrix(np.stack([A, B, Z]))
+    row = {"A": 0, "B": 1, "Z": 2}
+    sets = [np.array(c["members"]) for c in kat["cases"]]
+    nc = np.arange(*kat["nc"])
+    with Engine.from_cpm(X) as eng:
+        for mode in ("complement", "nc"):
+            eng.set_background(nc if mode == "nc" else None)
+            got = eng.run(sets)
+            for s, case in enumerate(kat["cases"]):
+                g = row[case["gene"]]
+                for name in ("up", "down", "fc", "cpm"):
+                    want = parse_float(case[mode][name])
+                    err = max_rel_err([got[name][s, g]], [want])
+                    assert err <= 1e-6, (case["gene"], mode, name, got[name][s, g], want)
+
+
+def test_hypergeom_kernel_vs_scipy_grid(hypergeom_grid, kat):
+    from pyspade_b200.engine import hypergeom_logcdf_logsf
+    g = hypergeom_grid
+    lc, ls = hypergeom_logcdf_logsf(g["k"], g["M"], g["n"], g["N"])
+    assert max_rel_err(lc, g["logcdf"]) <= LOGP_RTOL
+    assert max_rel_err(ls, g["logsf"]) <= LOGP_RTOL
+    for t in kat["hypergeom"]:
+        lc, ls = hypergeom_logcdf_logsf([t["k"]], [t["M"]], [t["n"]], [t["N"]])
+        assert max_rel_err(lc, [parse_float(t["logcdf"])]) <= LOGP_RTOL
+        assert max_rel_err(ls, [parse_float(t["logsf"])]) <= LOGP_RTOL
+
+
+def test_hypergeom_kernel_dense_sweep():
+    """every k of a few (M, n, N): support edges, both branches, far tails."""
+    from pyspade_b200.engine import hypergeom_logcdf_logsf
+    for (M, n, N) in [(60, 25, 17), (1000, 990, 50), (2000, 1100, 300), (50000, 46000, 500),
+                      (50000, 25001, 2000), (200000, 180000, 1000), (200000, 100003, 5000)]:
+        k = np.arange(-1, min(n, N) + 2)
+        lc, ls = hypergeom_logcdf_logsf(k, M, n, N)
+        wc, ws = c_oracle.hypergeom_logcdf_logsf(k, M, np.full_like(k, n), np.full_like(k, N))
+        assert max_rel_err(lc, wc) <= LOGP_RTOL, (M, n, N)
+        assert max_rel_err(ls, ws) <= LOGP_RTOL, (M, n, N)
+
+
+@pytest.mark.parametrize("mode", ["complement", "nc"])
+def test_mid_size_vs_oracle(mode):
+    """3000 cells x 900 genes, ragged sets incl. a single cell and C-1 cells."""
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 900, 3000
+    counts = synth.counts_numpy(G, C, seed=4)
+    rng = np.random.default_rng(8)
+    sizes = [1, 2, 33, 150, 700, 1500, 2999, 64, 64]
+    sets = [rng.choice(C, n, replace=False) for n in sizes]
+    nc = rng.choice(C, 120, replace=False) if mode == "nc" else None
+    with Engine.from_counts(counts) as eng:
+        eng.set_background(nc)
+        got = eng.run(sets, want_k=True)
+        med, n = eng.gene_cutoffs()
+        X = sp.csr_matrix((eng.cpm_values(), counts.indices, counts.indptr), shape=counts.shape)
+    Xo = de_port.cpm_normalization_port(counts)
+    assert np.array_equal(X.data, Xo.data)
+    ora = de_port.de_tables(Xo, sets, nc, tail_fn=c_oracle.hypergeom_logcdf_logsf)
+    assert np.array_equal(med, ora["median"])
+    assert np.array_equal(n, ora["n"])
+    assert np.array_equal(got["k"], ora["k"])
+    assert_tables_close(got, ora)
+
+
+def test_background_switch_is_idempotent():
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    counts = synth.counts_numpy(300, 800, seed=2)
+    sets = synth.deobs_sets(800, 5, lo=20, hi=200)
+    nc = np.arange(0, 800, 9)
+    with Engine.from_counts(counts) as eng:
+        a = eng.run(sets, want_k=True)
+        eng.set_background(nc)
+        b = eng.run(sets, want_k=True)
+        eng.set_background(None)
+        c = eng.run(sets, want_k=True)
+        eng.set_background(nc)
+        d = eng.run(sets, want_k=True)
+    for name in a:
+        assert np.array_equal(a[name], c[name], equal_nan=True)
+        assert np.array_equal(b[name], d[name], equal_nan=True)
+    assert not np.array_equal(a["fc"], b["fc"], equal_nan=True)
+
+
+def test_empty_and_degenerate_inputs():
+    from pyspade_b200.engine import Engine, SpadeError
+    X = sp.csr_matrix(np.array([[0, 0, 0, 0, 0], [1.5, 0, 2.5, 0, 0], [1, 1, 1, 1, 1]], dtype=np.float64))
+    with Engine.from_cpm(X) as eng:
+        out = eng.run([])                                   # no sets
+        assert out["up"].shape == (0, 3)
+        out = eng.run([np.array([], dtype=np.int64), np.array([0, 2])], want_k=True)
+        # empty set: N = 0 -> nan tails (all([k,M,n,N]) guard); means are 0/0 = nan like the reference
+        assert np.isnan(out["up"][0]).all() and np.isnan(out["down"][0]).all()
+        ora = de_port.de_tables(X, [np.array([0, 2])])
+        assert np.array_equal(out["k"][1], ora["k"][0])
+        assert_tables_close({k: v[1:] for k, v in out.items() if k != "k"}, ora)
+        with pytest.raises(IndexError):
+            eng.run([np.array([0, 5])])
+        with pytest.raises(ValueError):
+            eng.run([np.array([1, 1])])
+    # a matrix with no stored entries at all
+    with Engine.from_cpm(sp.csr_matrix((4, 7), dtype=np.float64)) as eng:
+        out = eng.run([np.array([1, 2, 3])], want_k=True)
+        assert (out["k"] == 3).all() and (out["up"] == 0).all() and np.isneginf(out["down"]).all()
+        assert (out["fc"] == 1.0).all() and (out["cpm"] == 0.0).all()
+
+
+def test_negative_values_general_matrix():
+    """The boundary takes any float64 matrix (perform_DE's input_array), not only CPM."""
+    from pyspade_b200.engine import Engine
+    rng = np.random.default_rng(12)
+    dense = rng.normal(0, 1, (40, 90)) * (rng.random((40, 90)) < 0.7)
+    dense[3] = -np.abs(dense[3]) - 0.1         # all negative: median < 0, zeros never low
+    dense[4, :] = 0.0
+    dense[4, :10] = -2.0
+    X = sp.csr_matrix(dense)
+    sets = [rng.choice(90, n, replace=False) for n in (5, 20, 45)]
+    with Engine.from_cpm(X) as eng:
+        got = eng.run(sets, want_k=True)
+        med, n = eng.gene_cutoffs()
+    ora = de_port.de_tables(X, sets)
+    assert np.array_equal(med, ora["median"]) and np.array_equal(n, ora["n"])
+    assert np.array_equal(got["k"], ora["k"])
+    for name in ("up", "down"):
+        assert max_rel_err(got[name], ora[name]) <= LOGP_RTOL
+
+
+def test_sharding_is_bit_identical():
+    """Sets split over several calls (what ranks do) give byte-identical tables."""
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    counts = synth.counts_numpy(500, 1200, seed=6)
+    sets = synth.derand_draws(1200, 60, 16)
+    with Engine.from_counts(counts) as eng:
+        whole = eng.run(sets, want_k=True)
+        parts = [eng.run(sets[r::4], want_k=True) for r in range(4)]
+    for name in whole:
+        for r in range(4):
+            assert np.array_equal(whole[name][r::4], parts[r][name], equal_nan=True)
