@@ -33,7 +33,8 @@ thread_local std::string g_create_error = "";
 constexpr int kStageThreads = 256;
 constexpr int kAccWarpsPerBlock = 8;
 constexpr int kFinThreads = 256;
-constexpr int64_t kMaxTestsPerChunk = int64_t(1) << 24;   // 16 Mi (gene, set) tests per chunk
+constexpr int64_t kMaxTestsPerChunk = int64_t(1) << 24;      // device outputs: 16 Mi tests per chunk
+constexpr int64_t kMaxTestsPerChunkHost = int64_t(1) << 22;  // host outputs: 4 Mi, copy/compute overlap
 constexpr double kTailEps = 1e-18;
 
 #define CUDA_TRY(expr)                                                                         \
@@ -496,8 +497,10 @@ struct spade_engine {
     DevBuf<int> acc_cnt;
     DevBuf<int32_t> members;
     DevBuf<int64_t> offsets;
-    DevBuf<double> out_f64;     // 4 tables of one chunk (host-output path)
-    DevBuf<int32_t> out_k;
+    DevBuf<double> out_f64[2];  // host-output path: 4 tables of one chunk, double-buffered
+    DevBuf<int32_t> out_k[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t buf_ready[2] = {nullptr, nullptr}, buf_free[2] = {nullptr, nullptr};
 
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -671,7 +674,16 @@ struct spade_engine {
         indptr.release(); colptr.release(); indices.release(); values.release(); cscpos.release();
         ent.release(); median.release(); bgmean.release(); lf.release(); n.release();
         negmode.release(); ncmask.release(); rowsum.release(); err.release(); acc_sum.release();
-        acc_cnt.release(); members.release(); offsets.release(); out_f64.release(); out_k.release();
+        acc_cnt.release(); members.release(); offsets.release(); 
+        for (int b = 0; b < 2; ++b) {
+            out_f64[b].release();
+            out_k[b].release();
+            if (buf_ready[b]) cudaEventDestroy(buf_ready[b]);
+            if (buf_free[b]) cudaEventDestroy(buf_free[b]);
+            buf_ready[b] = buf_free[b] = nullptr;
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        copy_stream = nullptr;
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear();
     }
@@ -890,19 +902,32 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
     CUDA_TRY(engine->offsets.reserve(S + 1));
     CUDA_TRY(cudaMemcpyAsync(engine->offsets.p, offsets, (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
 
-    const int64_t chunk_sets = std::max<int64_t>(1, std::min<int64_t>(S, kMaxTestsPerChunk / G));
+    const bool host_out = out_location == SPADE_HOST;
+    const int64_t chunk_cap = host_out ? kMaxTestsPerChunkHost : kMaxTestsPerChunk;
+    const int64_t chunk_sets = std::max<int64_t>(1, std::min<int64_t>(S, chunk_cap / G));
     CUDA_TRY(engine->acc_sum.reserve(chunk_sets * G));
     CUDA_TRY(engine->acc_cnt.reserve(chunk_sets * G));
-    const bool host_out = out_location == SPADE_HOST;
     if (host_out) {
-        CUDA_TRY(engine->out_f64.reserve(4 * chunk_sets * G));
-        CUDA_TRY(engine->out_k.reserve(chunk_sets * G));
+        // results leave through two device buffers: chunk i is copied to the host on
+        // copy_stream while chunk i+1 is computed on the caller's stream
+        if (!engine->copy_stream)
+            CUDA_TRY(cudaStreamCreateWithFlags(&engine->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(engine->out_f64[b].reserve(4 * chunk_sets * G));
+            if (k) CUDA_TRY(engine->out_k[b].reserve(chunk_sets * G));
+            if (!engine->buf_ready[b]) CUDA_TRY(cudaEventCreateWithFlags(&engine->buf_ready[b], cudaEventDisableTiming));
+            if (!engine->buf_free[b]) CUDA_TRY(cudaEventCreateWithFlags(&engine->buf_free[b], cudaEventDisableTiming));
+        }
     }
+    int64_t chunk_no = 0;
 
     for (int64_t s0 = 0; s0 < S; s0 += chunk_sets) {
         const int64_t s1 = std::min(S, s0 + chunk_sets);
         const int64_t tests = (s1 - s0) * G;
         const int64_t nmem = offsets[s1] - offsets[s0];
+        const int buf = (int)(chunk_no & 1);
+        if (host_out && chunk_no >= 2) CUDA_TRY(cudaStreamWaitEvent(st, engine->buf_free[buf], 0));
+        ++chunk_no;
         cudaEvent_t e0 = engine->next_event(), e1 = engine->next_event(), e2 = engine->next_event();
         if (!e0 || !e1 || !e2) { set_error("cudaEventCreate failed"); return SPADE_ERR_CUDA; }
         CUDA_TRY(cudaEventRecord(e0, st));
@@ -931,11 +956,11 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
         a.fix_inv = engine->fix_inv;
         const int64_t cs = chunk_sets * G;
         if (host_out) {
-            a.up = up ? engine->out_f64.p : nullptr;
-            a.down = down ? engine->out_f64.p + cs : nullptr;
-            a.fc = fc ? engine->out_f64.p + 2 * cs : nullptr;
-            a.cpm = cpm ? engine->out_f64.p + 3 * cs : nullptr;
-            a.k = k ? engine->out_k.p : nullptr;
+            a.up = up ? engine->out_f64[buf].p : nullptr;
+            a.down = down ? engine->out_f64[buf].p + cs : nullptr;
+            a.fc = fc ? engine->out_f64[buf].p + 2 * cs : nullptr;
+            a.cpm = cpm ? engine->out_f64[buf].p + 3 * cs : nullptr;
+            a.k = k ? engine->out_k[buf].p : nullptr;
         } else {
             a.up = up ? up + s0 * G : nullptr;
             a.down = down ? down + s0 * G : nullptr;
@@ -949,11 +974,15 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
         CUDA_TRY(cudaEventRecord(e2, st));
         if (host_out) {
             const size_t fb = tests * sizeof(double);
-            if (up) CUDA_TRY(cudaMemcpyAsync(up + s0 * G, a.up, fb, cudaMemcpyDeviceToHost, st));
-            if (down) CUDA_TRY(cudaMemcpyAsync(down + s0 * G, a.down, fb, cudaMemcpyDeviceToHost, st));
-            if (fc) CUDA_TRY(cudaMemcpyAsync(fc + s0 * G, a.fc, fb, cudaMemcpyDeviceToHost, st));
-            if (cpm) CUDA_TRY(cudaMemcpyAsync(cpm + s0 * G, a.cpm, fb, cudaMemcpyDeviceToHost, st));
-            if (k) CUDA_TRY(cudaMemcpyAsync(k + s0 * G, a.k, tests * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            cudaStream_t cs_ = engine->copy_stream;
+            CUDA_TRY(cudaEventRecord(engine->buf_ready[buf], st));
+            CUDA_TRY(cudaStreamWaitEvent(cs_, engine->buf_ready[buf], 0));
+            if (up) CUDA_TRY(cudaMemcpyAsync(up + s0 * G, a.up, fb, cudaMemcpyDeviceToHost, cs_));
+            if (down) CUDA_TRY(cudaMemcpyAsync(down + s0 * G, a.down, fb, cudaMemcpyDeviceToHost, cs_));
+            if (fc) CUDA_TRY(cudaMemcpyAsync(fc + s0 * G, a.fc, fb, cudaMemcpyDeviceToHost, cs_));
+            if (cpm) CUDA_TRY(cudaMemcpyAsync(cpm + s0 * G, a.cpm, fb, cudaMemcpyDeviceToHost, cs_));
+            if (k) CUDA_TRY(cudaMemcpyAsync(k + s0 * G, a.k, tests * sizeof(int32_t), cudaMemcpyDeviceToHost, cs_));
+            CUDA_TRY(cudaEventRecord(engine->buf_free[buf], cs_));
         }
         if (engine->ev_used > 3000) {            // bound the event pool on very long runs
             int rc = engine->collect_timing();
@@ -961,6 +990,7 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
         }
     }
     if (host_out) {
+        CUDA_TRY(cudaStreamSynchronize(engine->copy_stream));
         CUDA_TRY(cudaStreamSynchronize(st));
         return engine->check_device_error("spade_run");
     }
