@@ -17,10 +17,10 @@ One "step" = one pass of the hot path over that batch: 33 M (gene, draw) tests p
 ``e2e``     the same metric through the public API with HOST buffers: member index lists in
             host memory, result tables delivered to pinned host memory (H2D + kernels +
             D2H inside the timed region; + the NCCL gather and rank 0's D2H when N > 1).
-``roofline`` dominant kernel (k_accumulate): algorithmic bytes of SURVEY section 8-d
-            (rho * min(8 N, C/8) per test, the gather term) / its CUDA-event time, against the
-            measured HBM copy bandwidth of MEASURED_PEAKS.json; ``path`` = the whole path
-            (gather + 24 B of output per test) over accumulate + finalize time.
+``roofline`` dominant kernel (k_de_fused: member gather + tails + table writes in one
+            launch): algorithmic bytes of SURVEY section 8-d (rho * min(8 N, C/8) + 24 B per
+            test) / its CUDA-event time, against the measured HBM copy bandwidth of
+            MEASURED_PEAKS.json.
 ``cpu_baseline`` oracle per-gene port (oracle/de_port.py, kind "port": the Python reference
             cannot travel to the GPU box) on a bounded sample of the same workload, all host
             cores; the same sample is the parity check of the GPU tables (``parity``).
@@ -337,25 +337,22 @@ def main():
 
     # roofline of the dominant kernel (per rank; rank 0's kernel times)
     peak, peak_src = peaks()
-    chunk_sets = max(1, min(S, (1 << 24) // G))
-    launches_per_step = -(-S // chunk_sets)
+    launches_per_step = 1                      # one fused launch per step (+ the tail-table fill)
     gather_bytes, path_bytes = algorithmic_bytes(rho, [N] * S, C, G, B_OUT)
-    acc_ms = kt["accumulate_ms"] / args.steps
-    fin_ms = kt["finalize_ms"] / args.steps
-    achieved = gather_bytes / (acc_ms * 1e-3) / 1e9
-    path_achieved = path_bytes / ((acc_ms + fin_ms) * 1e-3) / 1e9
+    test_ms = kt["test_ms"] / args.steps
+    table_ms = kt["table_ms"] / args.steps
+    achieved = path_bytes / (test_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("k_accumulate_dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            traffic = json.load(fh).get("k_de_fused_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "k_de_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": gather_bytes / launches_per_step,
-                "launch_ms": acc_ms / launches_per_step, "launches_per_step": launches_per_step,
-                "path": {"achieved": path_achieved, "frac": path_achieved / peak,
-                         "bytes_per_test": path_bytes / (S * G), "accumulate_ms_per_step": acc_ms,
-                         "finalize_ms_per_step": fin_ms}}
+                "algorithmic_bytes_per_launch": path_bytes / launches_per_step,
+                "launch_ms": test_ms / launches_per_step, "launches_per_step": launches_per_step,
+                "bytes_per_test": path_bytes / (S * G), "gather_bytes_per_launch": gather_bytes,
+                "tail_table_ms_per_step": table_ms}
 
     line = None
     if rank == 0:
@@ -366,7 +363,7 @@ def main():
                                        f"(BASELINE.json configs[2], complement background)",
                            "cells": C, "genes": G, "draws_per_gpu": S, "set_size": N, "nnz": nnz,
                            "density": rho, "sharding": f"draws round-robin over {world} rank(s), matrix replicated",
-                           "l2": "inputs larger than L2: 1.0 GB cell-major matrix + 0.4 GB accumulators per step",
+                           "l2": "inputs larger than L2: 1.0 GB cell-major matrix read + 0.8 GB of tables written per step",
                            "stage_seconds": stage_s},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(world * (4 * S * N + 8 * (S + 1))),

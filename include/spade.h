@@ -42,7 +42,7 @@ extern "C" {
 #define SPADE_HOST 0
 #define SPADE_DEVICE 1
 
-#define SPADE_ABI_VERSION 1
+#define SPADE_ABI_VERSION 2
 
 typedef struct spade_engine spade_engine;
 
@@ -60,7 +60,7 @@ const char *spade_last_error(const spade_engine *engine);
  * per-row pickling (utils.py:303-307, 325-331), np.median over the dense row and
  * the low-set selection (utils.py:199-200).  One-time work per matrix:
  * per-gene median cutoff, n_g = #{cells <= median}, per-entry "above cutoff"
- * flags, row sums, and the cell-major (CSC) copy the batched test walks.
+ * flags, row sums, and the gene-partitioned cell-major copy the batched test walks.
  * Column indices inside a row must be unique; they need not be sorted.
  */
 int spade_create(int device, int64_t G, int64_t C, const int64_t *indptr, const int32_t *indices,
@@ -86,8 +86,25 @@ void spade_destroy(spade_engine *engine);
  */
 int spade_set_background(spade_engine *engine, const int32_t *nc_idx, int64_t n_nc);
 
-/* Matrix facts: G, C, stored non-zeros, and the fixed-point shift of the sums. */
-int spade_dims(const spade_engine *engine, int64_t *G, int64_t *C, int64_t *nnz, int32_t *fix_shift);
+/*
+ * Tuning / test knobs (defaults are right for production use):
+ *   SPADE_OPT_TAIL_TABLE      0 = evaluate every log-hypergeometric tail directly,
+ *                             1 = (default) per-run tail table when a batch of >= 32 sets
+ *                                 shares one set size N (DErand), 2 = table whenever a batch
+ *                                 shares one N.  Table entries are the direct evaluation
+ *                                 itself, so all three settings give bit-identical tables.
+ *   SPADE_OPT_MEMBER_BLOCK    member cells one warp accumulates before draining (1..32768,
+ *                             default 32768); sets larger than this take the split path.
+ *   SPADE_OPT_GENES_PER_PART  genes per partition of the cell-major layout (multiple of 32,
+ *                             <= 4096, 0 = default 1024); re-stages the matrix.
+ */
+#define SPADE_OPT_TAIL_TABLE 1
+#define SPADE_OPT_MEMBER_BLOCK 2
+#define SPADE_OPT_GENES_PER_PART 3
+int spade_set_option(spade_engine *engine, int option, int64_t value);
+
+/* Matrix facts: G, C, stored non-zeros, genes per partition of the staged layout. */
+int spade_dims(const spade_engine *engine, int64_t *G, int64_t *C, int64_t *nnz, int32_t *genes_per_part);
 
 /* Per-gene cutoffs for integer parity checks (host outputs, either may be NULL):
  * median[G] (float64) and n[G] = #{cells : x <= median} (int32). */
@@ -115,15 +132,20 @@ int spade_cpm_values(spade_engine *engine, double *values);
  *   out_location                 SPADE_HOST or SPADE_DEVICE for all five outputs
  *   stream                       cudaStream_t (as void*) the work is ordered on; NULL =
  *                                the legacy default stream.  With device outputs the call
- *                                returns without synchronising.
+ *                                returns without waiting for the kernels; with host outputs
+ *                                it returns when the tables are complete.
+ * Sets of any size are accepted (sets above SPADE_OPT_MEMBER_BLOCK cells take a slower
+ * split path).
  */
 int spade_run(spade_engine *engine, const int32_t *members, int members_location,
               const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
               int32_t *k, int out_location, void *stream);
 
-/* Kernel-time accounting (CUDA events on the launch stream, accumulated since
- * the last reset).  Synchronises.  launches = kernels launched by spade_run. */
-int spade_timing(spade_engine *engine, double *accumulate_ms, double *finalize_ms, int64_t *launches,
+/* Kernel-time accounting (CUDA events on the launch streams, accumulated since the last
+ * reset).  test_ms = the fused test kernel (member accumulation + tails + table writes;
+ * plus the split-path finalize), table_ms = tail-table builds.  Synchronises.
+ * launches = kernels launched by spade_run. */
+int spade_timing(spade_engine *engine, double *test_ms, double *table_ms, int64_t *launches,
                  int reset);
 
 /*

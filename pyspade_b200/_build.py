@@ -23,7 +23,8 @@ NVCC_FLAGS = [
 def needs_build() -> bool:
     if not os.path.isfile(OUT):
         return True
-    newest = max(os.path.getmtime(p) for p in (SRC, HDR))
+    deps = [HDR] + [os.path.join(os.path.dirname(SRC), f) for f in os.listdir(os.path.dirname(SRC))]
+    newest = max(os.path.getmtime(p) for p in deps)
     return os.path.getmtime(OUT) < newest
 
 

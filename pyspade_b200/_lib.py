@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_PKG, "libspade_b200.so")
 
 SPADE_OK, SPADE_ERR_ARG, SPADE_ERR_CUDA, SPADE_ERR_STATE = 0, 1, 2, 3
 SPADE_HOST, SPADE_DEVICE = 0, 1
-SPADE_ABI_VERSION = 1
+SPADE_ABI_VERSION = 2
+SPADE_OPT_TAIL_TABLE, SPADE_OPT_MEMBER_BLOCK, SPADE_OPT_GENES_PER_PART = 1, 2, 3
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64p = ctypes.POINTER(ctypes.c_int64)
@@ -29,6 +30,7 @@ SIGNATURES = {
                                                 ctypes.c_int, c_vpp]),
     "spade_destroy": (None, [ctypes.c_void_p]),
     "spade_set_background": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "spade_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]),
     "spade_dims": (ctypes.c_int, [ctypes.c_void_p, c_i64p, c_i64p, c_i64p, c_i32p]),
     "spade_gene_cutoffs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "spade_cpm_values": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -1,0 +1,225 @@
+// One-time staging kernels: K0 CPM normalisation, the gene-partitioned cell-major layout, and
+// K1 per-gene cutoffs / flags / fixed-point sums.  Reference lines: pySpade/utils.py:150-155
+// (cpm_normalization), :199-200 and :253-254 (median cutoff and low set).
+#pragma once
+#include "common.cuh"
+
+namespace spade {
+
+constexpr int kStageThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// K0: CPM normalisation (utils.py:150-155).  value = fl(fl(x * 1e6) * fl(1 / colsum)).
+// ------------------------------------------------------------------------------------------
+__global__ void k_col_sums(const int32_t *__restrict__ indices, const int32_t *__restrict__ counts,
+                           int64_t nnz, int64_t C, unsigned long long *__restrict__ colsum,
+                           int *__restrict__ err)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t c = indices[i];
+        if (c < 0 || c >= C) { atomicExch(err, 1); continue; }
+        atomicAdd(&colsum[c], (unsigned long long)(long long)counts[i]);
+    }
+}
+
+__global__ void k_cpm(const int32_t *__restrict__ indices, const int32_t *__restrict__ counts,
+                      int64_t nnz, int64_t C, const unsigned long long *__restrict__ colsum,
+                      double *__restrict__ values)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = indices[i];
+        if (c < 0 || c >= C) continue;                                    // flagged by k_col_sums
+        double inv = __drcp_rn((double)(long long)colsum[c]);             // fl(1/colsum)
+        values[i] = __dmul_rn(__dmul_rn((double)counts[i], 1e6), inv);    // no FMA contraction
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Layout: genes are cut into partitions of Gp consecutive genes; the stored values of
+// partition p are kept cell-major, segment (p, c) = ent[pptr[p*C + c] .. pptr[p*C + c + 1]).
+// One CTA per gene counts its entries per (partition, cell); an exclusive scan gives pptr.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStageThreads)
+k_part_hist(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, int64_t C,
+            int Gp, uint32_t *__restrict__ hist, int *__restrict__ err)
+{
+    const int64_t g = blockIdx.x;
+    const int64_t base = (g / Gp) * C;
+    for (int64_t i = indptr[g] + threadIdx.x; i < indptr[g + 1]; i += blockDim.x) {
+        const int32_t c = indices[i];
+        if (c < 0 || c >= C) { atomicExch(err, 1); continue; }
+        atomicAdd(&hist[base + c], 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: per-gene cutoff (utils.py:199-200, NC variant :253-254), flags, fixed-point sums.
+// One CTA per gene.  The cutoff is np.median over the scope (all C cells, or the NC cells),
+// zeros included: order statistics of the multiset {stored values in scope} + {implicit
+// zeros}, found with an 8-bit-per-pass radix select on order-preserving keys of the float64
+// values.  The same CTA then writes the gene's packed entries into the partitioned layout.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long order_key(double v)
+{
+    if (v == 0.0) v = 0.0;   // -0.0 and +0.0 share a key
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ double key_value(unsigned long long k)
+{
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+struct StageArgs {
+    const int64_t *indptr;
+    const int32_t *indices;
+    const double *values;
+    const uint8_t *ncmask;    // null -> scope = all cells
+    int64_t C;
+    int64_t scope_len;        // C or |NC|
+    int Gp;
+    uint32_t *cursor;         // running write position of every (partition, cell) segment
+    unsigned long long *ent;
+    double *median;
+    int32_t *n;
+    GeneMeta *meta;
+    int *err;
+};
+
+__device__ double block_select(const StageArgs &a, int64_t beg, int64_t end, int64_t implicit_zeros,
+                               int64_t rank, unsigned long long *hist /*256*/,
+                               unsigned long long *bcast /*2*/)
+{
+    const unsigned long long zkey = order_key(0.0);
+    unsigned long long prefix = 0;
+    for (int pass = 7; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+            if (a.ncmask && !a.ncmask[a.indices[i]]) continue;
+            unsigned long long key = order_key(a.values[i]);
+            bool match = (pass == 7) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+            if (match) atomicAdd(&hist[(key >> shift) & 255], 1ull);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bool zmatch = (pass == 7) || ((zkey >> (shift + 8)) == (prefix >> (shift + 8)));
+            if (zmatch) hist[(zkey >> shift) & 255] += (unsigned long long)implicit_zeros;
+            unsigned long long r = (unsigned long long)rank, cum = 0;
+            int bin = 255;
+            for (int b = 0; b < 256; ++b) {
+                if (cum + hist[b] > r) { bin = b; break; }
+                cum += hist[b];
+            }
+            bcast[0] = prefix | ((unsigned long long)bin << shift);
+            bcast[1] = r - cum;
+        }
+        __syncthreads();
+        prefix = bcast[0];
+        rank = (int64_t)bcast[1];
+        __syncthreads();
+    }
+    return key_value(prefix);
+}
+
+__global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
+{
+    __shared__ unsigned long long hist[256];
+    __shared__ unsigned long long bcast[2];
+    __shared__ long long scratch_ll[33];
+    __shared__ double scratch_d[33];
+
+    const int64_t g = blockIdx.x;
+    const int64_t beg = a.indptr[g], end = a.indptr[g + 1];
+
+    // pass 0: census of the scope, magnitude of the row
+    long long in_scope = 0, neg = 0, pos = 0;
+    double rowabs = 0.0, maxabs = 0.0;
+    bool bad = false;
+    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        const double v = a.values[i];
+        const double av = fabs(v);
+        bad |= !(av < 8.0e270);                   // nan, inf, or too large for the fixed point
+        rowabs += av;
+        maxabs = fmax(maxabs, av);
+        if (a.ncmask && !a.ncmask[a.indices[i]]) continue;
+        ++in_scope;
+        neg += v < 0.0;
+        pos += v > 0.0;
+    }
+    if (bad) atomicExch(a.err, 3);
+    in_scope = block_sum(in_scope, scratch_ll);
+    neg = block_sum(neg, scratch_ll);
+    pos = block_sum(pos, scratch_ll);
+    rowabs = block_sum(rowabs, scratch_d);
+    maxabs = block_max(maxabs, scratch_d);
+    const int64_t L = a.scope_len;
+    const int64_t implicit_zeros = L - in_scope;
+    const int64_t zeros = L - neg - pos;            // implicit + explicitly stored zeros
+    const int64_t lo_i = (L - 1) / 2, hi_i = L / 2;
+
+    double m = 0.0;
+    if (L > 0) {
+        const bool lo_zero = lo_i >= neg && lo_i < neg + zeros;
+        const bool hi_zero = hi_i >= neg && hi_i < neg + zeros;
+        double va = lo_zero ? 0.0 : block_select(a, beg, end, implicit_zeros, lo_i, hist, bcast);
+        double vb = (hi_i == lo_i) ? va
+                    : (hi_zero ? 0.0 : block_select(a, beg, end, implicit_zeros, hi_i, hist, bcast));
+        m = (hi_i == lo_i) ? va : __dmul_rn(__dadd_rn(va, vb), 0.5);   // np.median: fl(a+b)/2
+    }
+    const bool negmode = m < 0.0;
+
+    // Fixed point of this gene: any sum over <= kMemberBlock member cells stays below 2^46.
+    //   bound = min(sum |v|, kMemberBlock * max |v|) < 2^e   ->   shift = 45 - e
+    int shift = 0;
+    {
+        const double bound = fmin(rowabs, (double)kMemberBlock * maxabs);
+        if (bound > 0.0 && !bad) {
+            int e;
+            frexp(bound, &e);
+            shift = min(900, max(-900, 45 - e));
+        }
+    }
+
+    const int64_t part = g / a.Gp;
+    const unsigned long long slot = (unsigned long long)(g - part * a.Gp) << kFieldBits;
+    uint32_t *cursor = a.cursor + part * a.C;
+    long long n_low = 0, rowsum = 0, bgsum = 0;
+    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        const double v = a.values[i];
+        const int32_t c = a.indices[i];
+        const long long fx = bad ? 0ll : __double2ll_rn(scalbn(v, shift));
+        const bool low = v <= m;
+        n_low += low;
+        rowsum += fx;
+        if (a.ncmask && a.ncmask[c]) bgsum += fx;
+        const long long flag = negmode ? (low ? 1 : 0) : (low ? 0 : 1);
+        const unsigned long long field =
+            (unsigned long long)((flag << kCountShift) + fx) & ((1ull << kFieldBits) - 1);
+        const uint32_t at = atomicAdd(&cursor[c], 1u);
+        a.ent[at] = slot | field;
+    }
+    n_low = block_sum(n_low, scratch_ll);
+    rowsum = block_sum(rowsum, scratch_ll);
+    bgsum = block_sum(bgsum, scratch_ll);
+    if (threadIdx.x == 0) {
+        const int32_t n = (int32_t)(n_low + ((0.0 <= m) ? (a.C - (end - beg)) : 0));
+        a.median[g] = m;
+        a.n[g] = n;
+        GeneMeta mt;
+        mt.n = n;
+        mt.shift = (int16_t)shift;
+        mt.negmode = negmode ? 1 : 0;
+        mt.pad = 0;
+        if (a.ncmask) mt.bgmean = ((double)bgsum * pow2_double(-shift)) * (1.0 / (double)L);
+        else mt.rowsum = rowsum;
+        a.meta[g] = mt;
+    }
+}
+
+}  // namespace spade

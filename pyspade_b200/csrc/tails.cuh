@@ -1,0 +1,97 @@
+// K3: log-hypergeometric tails with scipy's definition (scipy/stats/_discrete_distns.py,
+// hypergeom_gen._logcdf/_logsf, restated in oracle/hypergeom_port.py), and the per-run
+// tail table used when every cell set of a batch has the same size N (DErand).
+#pragma once
+#include "common.cuh"
+
+namespace spade {
+
+constexpr double kTailEps = 1e-18;
+
+__device__ __forceinline__ double ln_choose(const double *__restrict__ lf, int a, int b)
+{
+    return lf[a] - lf[b] - lf[a - b];
+}
+
+// logcdf = ln P(X <= k), logsf = ln P(X > k), X ~ Hypergeom(M, n, N).
+// The tail on the far side of the mean is summed directly as pmf(edge) * (1 + r + r r' + ...),
+// the ratio recurrence in float64 anchored at a log-factorial-table log pmf; the near side is
+// log1p(-exp(far side)) - the branch rule of scipy, so values next to 0 keep their precision.
+__device__ void hyper_tails(int k, int M, int n, int N, const double *__restrict__ lf,
+                            double &logcdf, double &logsf)
+{
+    const int a = max(N - (M - n), 0), b = min(n, N);
+    if (k >= b) { logcdf = 0.0; logsf = -INFINITY; return; }
+    if (k < a)  { logcdf = -INFINITY; logsf = 0.0; return; }
+    const double ln_total = ln_choose(lf, M, N);
+    const bool upper_small = ((double)k + 0.5) * ((double)M + 0.5) > ((double)n - 0.5) * ((double)N - 0.5);
+    double t = 1.0, sum = 1.0;
+    if (upper_small) {
+        const int j = k + 1;
+        const double lp = ln_choose(lf, n, j) + ln_choose(lf, M - n, N - j) - ln_total;
+        double fa = (double)(n - j), fb = (double)(N - j), fc = (double)(j + 1),
+               fd = (double)(M - n - N + j + 1);
+        while (fa > 0.0 && fb > 0.0) {
+            t *= (fa * fb) / (fc * fd);
+            sum += t;
+            if (t < sum * kTailEps) break;
+            fa -= 1.0; fb -= 1.0; fc += 1.0; fd += 1.0;
+        }
+        logsf = lp + log(sum);
+        logcdf = log1p(-exp(logsf));
+    } else {
+        const int j = k;
+        const double lp = ln_choose(lf, n, j) + ln_choose(lf, M - n, N - j) - ln_total;
+        double fa = (double)j, fb = (double)(M - n - N + j), fc = (double)(n - j + 1),
+               fd = (double)(N - j + 1);
+        while (fa > 0.0 && fb > 0.0) {
+            t *= (fa * fb) / (fc * fd);
+            sum += t;
+            if (t < sum * kTailEps) break;
+            fa -= 1.0; fb -= 1.0; fc += 1.0; fd += 1.0;
+        }
+        logcdf = lp + log(sum);
+        logsf = log1p(-exp(logcdf));
+    }
+}
+
+// Tail table: for gene g and k in [lo_g, lo_g + len_g) the pair (logcdf, logsf) of
+// Hypergeom(M, n_g, N).  Entries are hyper_tails() itself, so a looked-up value is
+// bit-identical to a directly evaluated one.  One warp per gene.
+__global__ void __launch_bounds__(256)
+k_tail_table(const TabMeta *__restrict__ tmeta, const GeneMeta *__restrict__ meta, int64_t G,
+             int M, int N, const double *__restrict__ lf, double2 *__restrict__ tab)
+{
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= G) return;
+    const TabMeta t = tmeta[g];
+    const int n = meta[g].n;
+    for (int i = lane; i < t.len; i += 32) {
+        double lc, ls;
+        hyper_tails(t.lo + i, M, n, N, lf, lc, ls);
+        tab[t.off + i] = make_double2(lc, ls);
+    }
+}
+
+__global__ void k_hyper_probe(const int64_t *__restrict__ k, const int64_t *__restrict__ M,
+                              const int64_t *__restrict__ n, const int64_t *__restrict__ N,
+                              int64_t count, const double *__restrict__ lf,
+                              double *__restrict__ logcdf, double *__restrict__ logsf)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t kk = k[i], MM = M[i], nn = n[i], NN = N[i];
+    double lc, ls;
+    if (!(MM > 0 && nn >= 0 && NN >= 0 && nn <= MM && NN <= MM)) {
+        lc = ls = __longlong_as_double(0x7ff8000000000000ll);
+    } else {
+        // clamp k into int range around the support; the clamps in hyper_tails decide
+        const int64_t kc = kk < -1 ? -1 : (kk > MM ? MM : kk);
+        hyper_tails((int)kc, (int)MM, (int)nn, (int)NN, lf, lc, ls);
+    }
+    logcdf[i] = lc;
+    logsf[i] = ls;
+}
+
+}  // namespace spade

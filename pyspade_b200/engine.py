@@ -64,7 +64,7 @@ class Engine:
         f = ctypes.c_int32()
         self._check(self._lib.spade_dims(self._h, ctypes.byref(G), ctypes.byref(C),
                                          ctypes.byref(nnz), ctypes.byref(f)))
-        self.G, self.C, self.nnz, self.fix_shift = G.value, C.value, nnz.value, f.value
+        self.G, self.C, self.nnz, self.genes_per_part = G.value, C.value, nnz.value, f.value
         self.n_nc = 0
 
     # ------------------------------------------------------------------ construction
@@ -141,6 +141,19 @@ class Engine:
 
     def __exit__(self, *exc):
         self.close()
+
+    # ------------------------------------------------------------------ knobs
+    def set_option(self, name, value):
+        """``tail_table`` (0 direct / 1 auto / 2 always-when-uniform), ``member_block``
+        (cells per warp before draining; larger sets take the split path),
+        ``genes_per_part`` (re-stages the layout).  See ``spade_set_option``."""
+        opt = {"tail_table": _lib.SPADE_OPT_TAIL_TABLE, "member_block": _lib.SPADE_OPT_MEMBER_BLOCK,
+               "genes_per_part": _lib.SPADE_OPT_GENES_PER_PART}[name]
+        self._check(self._lib.spade_set_option(self._h, opt, int(value)))
+        if name == "genes_per_part":
+            f = ctypes.c_int32()
+            self._check(self._lib.spade_dims(self._h, None, None, None, ctypes.byref(f)))
+            self.genes_per_part = f.value
 
     # ------------------------------------------------------------------ background
     def set_background(self, nc_idx=None):
@@ -254,7 +267,7 @@ class Engine:
         a, f, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
         self._check(self._lib.spade_timing(self._h, ctypes.byref(a), ctypes.byref(f),
                                            ctypes.byref(n), 1 if reset else 0))
-        return dict(accumulate_ms=a.value, finalize_ms=f.value, launches=n.value)
+        return dict(test_ms=a.value, table_ms=f.value, launches=n.value)
 
 
 def hypergeom_logcdf_logsf(k, M, n, N, device=0):

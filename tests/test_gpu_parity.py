@@ -199,3 +199,118 @@ def test_sharding_is_bit_identical():
     for name in whole:
         for r in range(4):
             assert np.array_equal(whole[name][r::4], parts[r][name], equal_nan=True)
+
+
+def _tables_equal(a, b):
+    for name in a:
+        assert np.array_equal(a[name], b[name], equal_nan=True), name
+
+
+def test_tail_table_and_direct_paths_are_bit_identical():
+    """Uniform-N batch (DErand shape): per-run tail table vs direct evaluation; includes
+    extreme (non-random) sets whose k falls outside the table window."""
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C, N = 700, 4000, 150
+    counts = synth.counts_numpy(G, C, seed=9)
+    sets = synth.derand_draws(C, N, 40)
+    depth = np.asarray(counts.sum(axis=0)).ravel()
+    order = np.argsort(depth)
+    sets += [order[:N], order[-N:], order[C // 2:C // 2 + N]]     # shallowest / deepest cells
+    X = de_port.cpm_normalization_port(counts)
+    ora = de_port.de_tables(X, sets, tail_fn=c_oracle.hypergeom_logcdf_logsf)
+    with Engine.from_counts(counts) as eng:
+        res = {}
+        for mode in (0, 1, 2):
+            eng.set_option("tail_table", mode)
+            res[mode] = eng.run(sets, want_k=True)
+        assert eng.timing()["table_ms"] > 0.0
+    _tables_equal(res[0], res[1])
+    _tables_equal(res[0], res[2])
+    assert np.array_equal(res[1]["k"], ora["k"])
+    assert_tables_close(res[1], ora)
+
+
+@pytest.mark.parametrize("mode", ["complement", "nc"])
+def test_split_path_small_member_block(mode):
+    """Sets larger than the member block go through global accumulators (split path)."""
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 400, 1500
+    counts = synth.counts_numpy(G, C, seed=13)
+    rng = np.random.default_rng(3)
+    sets = [rng.choice(C, n, replace=False) for n in (5, 64, 65, 300, 1499, 0)]
+    nc = rng.choice(C, 90, replace=False) if mode == "nc" else None
+    with Engine.from_counts(counts) as eng:
+        eng.set_background(nc)
+        whole = eng.run(sets, want_k=True)
+        eng.set_option("member_block", 64)
+        split = eng.run(sets, want_k=True)
+    _tables_equal(whole, split)
+    X = de_port.cpm_normalization_port(counts)
+    ora = de_port.de_tables(X, sets[:-1], nc, tail_fn=c_oracle.hypergeom_logcdf_logsf)
+    assert np.array_equal(split["k"][:-1], ora["k"])
+    assert_tables_close({k: v[:-1] for k, v in split.items() if k != "k"}, ora)
+
+
+def test_set_larger_than_default_member_block():
+    """N > 32768 member cells: the count field of a warp accumulator would overflow, the
+    split path must take over on its own."""
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 64, 40000
+    counts = synth.counts_numpy(G, C, seed=5)
+    counts = sp.csr_matrix(counts.toarray() + (np.arange(G)[:, None] % 4 == 0))   # some dense genes
+    rng = np.random.default_rng(1)
+    sets = [rng.choice(C, n, replace=False) for n in (36000, 100, 39999)]
+    with Engine.from_counts(counts) as eng:
+        got = eng.run(sets, want_k=True)
+    X = de_port.cpm_normalization_port(counts)
+    ora = de_port.de_tables(X, sets, tail_fn=c_oracle.hypergeom_logcdf_logsf)
+    assert np.array_equal(got["k"], ora["k"])
+    assert_tables_close(got, ora)
+
+
+@pytest.mark.parametrize("gp", [32, 96, 1024, 4096])
+def test_partition_width_does_not_change_results(gp):
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 1300, 2500
+    counts = synth.counts_numpy(G, C, seed=21)
+    sets = synth.deobs_sets(C, 12, lo=10, hi=900)
+    nc = np.arange(3, C, 17)
+    with Engine.from_counts(counts) as eng:
+        eng.set_background(nc)
+        base = eng.run(sets, want_k=True)
+        eng.set_option("genes_per_part", gp)
+        assert eng.genes_per_part == min(gp, 1312)
+        eng.set_background(nc)
+        other = eng.run(sets, want_k=True)
+    _tables_equal(base, other)
+
+
+def test_device_outputs_match_host_outputs():
+    """spade_run with device members / device tables (bench path) vs host tables."""
+    import torch
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 2100, 3000
+    counts = synth.counts_numpy(G, C, seed=31)
+    sets = synth.derand_draws(C, 120, 70)
+    members, offsets = synth.concat_sets(sets)
+    with Engine.from_counts(counts) as eng:
+        host = eng.run(sets, want_k=True)
+        out = {k: torch.empty((len(sets), G), dtype=torch.float64, device="cuda") for k in ("up", "down", "fc", "cpm")}
+        kd = torch.empty((len(sets), G), dtype=torch.int32, device="cuda")
+        eng.run_device(torch.from_numpy(members).cuda(), offsets, out, k=kd)
+        torch.cuda.synchronize()
+    for name in out:
+        assert np.array_equal(out[name].cpu().numpy(), host[name], equal_nan=True), name
+    assert np.array_equal(kd.cpu().numpy(), host["k"])
+
+
+def test_non_finite_values_are_refused():
+    from pyspade_b200.engine import Engine, SpadeError
+    X = sp.csr_matrix(np.array([[1.0, np.inf, 0.0], [0.0, 2.0, 3.0]]))
+    with pytest.raises(SpadeError):
+        Engine.from_cpm(X)
