@@ -1,0 +1,169 @@
+"""``pySpade DErand``: DE of random cell draws, the empirical background (mirror of
+``pySpade/DErand.py:30-304``).  The draws come from the same legacy numpy RNG calls in the
+same order, so the selected cells are identical to the reference's; all draws are then
+tested in one batch on the GPU (sharded by draw when launched under torchrun), and the
+final files are written once instead of after every draw (``DErand.py:224-248`` rewrites
+them each iteration; the last write is what stays on disk).
+"""
+import multiprocessing
+import os
+import sys
+
+import numpy as np
+import scipy.stats as stats
+
+from . import io as spio
+from . import shard
+from .engine import Engine
+from .utils import find_all_sgrna_cells, get_logger, get_num_processes, read_sgrna_dict
+
+np.random.seed(0)                       # DErand.py:27
+logger = get_logger(logger_name=__name__)
+
+
+def _gamma_fit_column(neg_logp):
+    """One gene of ``DErand.py:263-276``: ``None`` = leave the zeros, else (a, b, c)."""
+    finite = neg_logp[np.isfinite(neg_logp)]
+    if finite.shape[0] <= 50:
+        return None
+    if np.all(finite == finite[0]):
+        return (np.nan, 0.0, 1.0)
+    return stats.gamma.fit(finite)
+
+
+def _gamma_fit_chunk(neg_table):
+    return [_gamma_fit_column(neg_table[:, j]) for j in range(neg_table.shape[1])]
+
+
+def gamma_parameters(table, what, processes=None):
+    """Per-gene ``scipy.stats.gamma.fit`` of ``-log p`` over the draws (the unchanged
+    arithmetic of ``DErand.py:250-292``), genes farmed out to worker processes."""
+    S, G = table.shape
+    A, B, C = np.zeros(G), np.zeros(G), np.zeros(G)
+    neg = -table
+    processes = processes or get_num_processes()
+    chunk = 256
+    spans = [(g0, min(G, g0 + chunk)) for g0 in range(0, G, chunk)]
+    if processes > 1 and G * S >= 200000:
+        with multiprocessing.get_context("spawn").Pool(processes) as pool:
+            parts = pool.map(_gamma_fit_chunk, [neg[:, a:b] for a, b in spans])
+    else:
+        parts = [_gamma_fit_chunk(neg[:, a:b]) for a, b in spans]
+    for (a, b), part in zip(spans, parts):
+        for j, fit in enumerate(part):
+            if (a + j) % 10000 == 0:
+                logger.info('Finished ' + str(a + j) + ' genes.')
+            if fit is not None:
+                A[a + j], B[a + j], C[a + j] = fit
+    return A, B, C
+
+
+def DE_random_cells(sub_df_file,
+                    sgrna_df,
+                    sgrnas_file,
+                    num_cell,
+                    RAND_M,
+                    output_dir,
+                    iteration=1000,
+                    num_processing=1,
+                    norm='cpm',
+                    background_cells='complement'):
+    rank, local_rank, world = shard.world()
+    logger.info(f'B200 engine on {world} GPU rank(s); --threads is ignored (DErand.py:41).')
+
+    if (norm != 'cpm') and (norm != 'metacell'):
+        logger.critical("Incorrect normalization method. Has to be either 'cpm' or 'metacell'")
+        sys.exit(0)
+    if norm == 'metacell':
+        logger.critical("'metacell' normalization is not available (broken in pySpade 0.1.7). Job cancels.")
+        sys.exit(0)
+    if (RAND_M != 'equal') and (RAND_M != 'sgrna'):
+        logger.critical("Incorrect randomization method. Has to be either 'equal' or 'sgrna'")
+        sys.exit(0)
+
+    logger.info('Reading transcriptome file.')
+    trans_df = spio.read_frame(sub_df_file)
+    columns = trans_df.columns
+    counts = spio.frame_to_csr(trans_df)
+    del trans_df
+    G = counts.shape[0]
+    engine = Engine.from_counts(counts, device=local_rank)
+    del counts
+    logger.info('Finished transcriptome normalization.')
+
+    sgrna_df_adj_bool = (spio.read_frame(sgrna_df) > 0)
+    [g, c] = sgrna_df_adj_bool.shape
+    assert np.sum(columns == sgrna_df_adj_bool.columns) == c
+    if RAND_M == 'sgrna':
+        per_cell = np.asarray(sgrna_df_adj_bool.sum(axis=0).values, dtype=np.int64)
+        total_choose_num = per_cell.sum()
+        sgrna_weight_list_un = np.array(list(per_cell / total_choose_num))
+        sgrna_weight_list = sgrna_weight_list_un / np.sum(sgrna_weight_list_un)
+    logger.info('Finished processing sgRNA df.')
+
+    population = np.arange(c)
+    weights = sgrna_weight_list if RAND_M == 'sgrna' else None
+    if background_cells != 'complement':
+        sgrna_dict = read_sgrna_dict(sgrnas_file)
+        if background_cells not in sgrna_dict:
+            logger.critical('Background region is not in sgRNA dictionary text file. Please fix the '
+                            'dictionary file or use default parameter. Job cancels.')
+            raise KeyError(background_cells)
+        missing_NC_list = list(set(sgrna_dict[background_cells]) - set(sgrna_df_adj_bool.index))
+        remain_NC_list = list(set(sgrna_dict[background_cells]) - (set(missing_NC_list)))
+        logger.info(str(len(remain_NC_list)) + ' sgRNAs remain to find background cells.')
+        sgrna_dict.update({background_cells: remain_NC_list})
+        NC_idx = find_all_sgrna_cells(sgrna_df_adj_bool, sgrna_dict[background_cells])
+        if len(NC_idx) == 0:
+            logger.critical('No cell as background. Please consider other background set. Job cancels.')
+            sys.exit(0)
+        logger.info(str(len(NC_idx)) + ' cells as background for differential expression analysis.')
+        engine.set_background(NC_idx)
+        population = np.setxor1d(np.arange(c), NC_idx)              # DErand.py:129-133
+        if weights is not None:
+            weights = sgrna_weight_list[list(population)]
+            weights /= weights.sum()
+    del sgrna_df_adj_bool
+
+    # The draws: the reference's RNG calls, in the reference's order, before any sharding.
+    logger.info('Start randomization Calculation.')
+    draws = []
+    for i in np.arange(iteration):
+        if i % 25 == 0:
+            logger.info('Finished ' + str(i) + ' iterations.')
+        if weights is not None:
+            draws.append(np.random.choice(population, size=num_cell, replace=False, p=weights))
+        else:
+            draws.append(np.random.choice(population, size=num_cell, replace=False))
+
+    res = shard.run_sharded(engine, draws, tables=("up", "down", "cpm"))
+    engine.close()
+    if rank != 0:
+        return
+
+    spio.write_cell_ids(output_dir + '/' + str(num_cell) + '-rand_cell_ID.txt', draws)
+    spio.save_draw_table('%s/%s-up_log-pval' % (output_dir, num_cell), res["up"])
+    spio.save_draw_table('%s/%s-down_log-pval' % (output_dir, num_cell), res["down"])
+    spio.save_draw_table('%s/%s-cpm' % (output_dir, num_cell), res["cpm"])
+
+    logger.info('Start modeling randomization distribution.')
+    cpm_mean = np.mean(res["cpm"], axis=0)
+    logger.info('Process up-regulation.')
+    A, B, C = gamma_parameters(res["up"], 'up')
+    logger.info('Process down-regulation.')
+    D, E, F = gamma_parameters(res["down"], 'down')
+
+    # string concatenation as in DErand.py:295-302: output_dir must end with '/'
+    np.save(output_dir + 'Up_dist_gamma-%s-A' % (num_cell), A)
+    np.save(output_dir + 'Up_dist_gamma-%s-B' % (num_cell), B)
+    np.save(output_dir + 'Up_dist_gamma-%s-C' % (num_cell), C)
+    np.save(output_dir + 'Down_dist_gamma-%s-A' % (num_cell), D)
+    np.save(output_dir + 'Down_dist_gamma-%s-B' % (num_cell), E)
+    np.save(output_dir + 'Down_dist_gamma-%s-C' % (num_cell), F)
+    np.save(output_dir + 'Cpm_mean-%s' % (num_cell), cpm_mean)
+
+    logger.info('Job is done.')
+
+
+if __name__ == '__main__':
+    pass

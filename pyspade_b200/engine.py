@@ -66,6 +66,7 @@ class Engine:
                                          ctypes.byref(nnz), ctypes.byref(f)))
         self.G, self.C, self.nnz, self.genes_per_part = G.value, C.value, nnz.value, f.value
         self.n_nc = 0
+        self.background_key = None
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -162,10 +163,13 @@ class Engine:
         if nc_idx is None or len(nc_idx) == 0:
             self._check(self._lib.spade_set_background(self._h, None, 0))
             self.n_nc = 0
+            self.background_key = None
             return
-        nc = np.ascontiguousarray(np.asarray(nc_idx), dtype=np.int32)
+        key = np.ascontiguousarray(np.asarray(nc_idx), dtype=np.int64)
+        nc = key.astype(np.int32)
         self._check(self._lib.spade_set_background(self._h, _ptr(nc), nc.shape[0]))
         self.n_nc = int(nc.shape[0])
+        self.background_key = key.tobytes()
 
     # ------------------------------------------------------------------ parity probes
     def gene_cutoffs(self):
