@@ -35,16 +35,16 @@ def _gamma_fit_chunk(neg_table):
     return [_gamma_fit_column(neg_table[:, j]) for j in range(neg_table.shape[1])]
 
 
-def gamma_parameters(table, what, processes=None):
+def gamma_parameters(table, what, processes=None, min_pool_work=200000):
     """Per-gene ``scipy.stats.gamma.fit`` of ``-log p`` over the draws (the unchanged
     arithmetic of ``DErand.py:250-292``), genes farmed out to worker processes."""
     S, G = table.shape
     A, B, C = np.zeros(G), np.zeros(G), np.zeros(G)
     neg = -table
     processes = processes or get_num_processes()
-    chunk = 256
+    chunk = 256 if G >= 2048 else 32
     spans = [(g0, min(G, g0 + chunk)) for g0 in range(0, G, chunk)]
-    if processes > 1 and G * S >= 200000:
+    if processes > 1 and G * S >= min_pool_work:
         with multiprocessing.get_context("spawn").Pool(processes) as pool:
             parts = pool.map(_gamma_fit_chunk, [neg[:, a:b] for a, b in spans])
     else:

@@ -70,6 +70,7 @@ struct spade_engine {
     int tail_mode = 1;                 // 0 never, 1 auto, 2 whenever the batch has one set size
     int member_block = kMemberBlock;
     int gp_request = 0;                // 0 = default
+    int bank_order = 1;                // lay segments out for conflict-free accumulator access
 
     DevBuf<int64_t> indptr;
     DevBuf<int32_t> indices;
@@ -183,6 +184,12 @@ struct spade_engine {
         a.err = err.p;
         if (G > 0) k_gene_stage<<<(unsigned)G, kStageThreads, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
+        if (nnz > 0 && bank_order) {
+            const int64_t nseg = (int64_t)P * C;
+            k_bank_order<<<(unsigned)((nseg + kOrderWarps - 1) / kOrderWarps), kOrderWarps * 32, 0, st>>>(
+                pptr.p, nseg, ent.p);
+            CUDA_TRY(cudaGetLastError());
+        }
         h_n.resize((size_t)G);
         if (G > 0)
             CUDA_TRY(cudaMemcpyAsync(h_n.data(), n.p, G * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -388,6 +395,7 @@ int create_common(int device, int64_t G, int64_t C, const int64_t *indptr, const
     e->G = G;
     e->C = C;
     if (const char *gp = getenv("SPADE_GENES_PER_PART")) e->gp_request = atoi(gp);
+    if (const char *bo = getenv("SPADE_BANK_ORDER")) e->bank_order = atoi(bo) != 0;
     auto bail = [&](int code) {
         g_create_error = e->error;
         e->free_all();

@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 print(f"synth {time.time()-t0:.2f}s nnz={indices.numel()} density={indices.numel()/(a.G*a.C):.4f}")
 t0 = time.time()
 eng = Engine.from_device_csr(a.G, a.C, indptr, indices, counts, device=0)
-print(f"stage {time.time()-t0:.2f}s fix_shift={eng.fix_shift}")
+print(f"stage {time.time()-t0:.2f}s genes_per_part={eng.genes_per_part}")
 draws = synth.derand_draws(a.C, a.N, a.S)
 members, offsets = synth.concat_sets(draws)
 dm = torch.from_numpy(members).to(dev)
@@ -37,7 +37,7 @@ for rep in range(a.reps):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     t = eng.timing()
-    print(f"rep{rep}: total {ms:.2f} ms  acc {t['accumulate_ms']:.2f}  fin {t['finalize_ms']:.2f}  "
+    print(f"rep{rep}: total {ms:.2f} ms  test {t['test_ms']:.2f}  table {t['table_ms']:.2f}  "
           f"tests/s {a.S*a.G/ms*1e3:.3e}")
 # host path
 t0 = time.time()
