@@ -97,10 +97,14 @@ int spade_set_background(spade_engine *engine, const int32_t *nc_idx, int64_t n_
  *                             default 32768); sets larger than this take the split path.
  *   SPADE_OPT_GENES_PER_PART  genes per partition of the cell-major layout (multiple of 32,
  *                             <= 4096, 0 = default 1024); re-stages the matrix.
+ *   SPADE_OPT_SORT_MEMBERS    1 = (default) visit the cells of every set in ascending order
+ *                             (device-side segmented sort of a copy of the member lists;
+ *                             better L2 locality), 0 = keep the caller's order.  Same tables.
  */
 #define SPADE_OPT_TAIL_TABLE 1
 #define SPADE_OPT_MEMBER_BLOCK 2
 #define SPADE_OPT_GENES_PER_PART 3
+#define SPADE_OPT_SORT_MEMBERS 4
 int spade_set_option(spade_engine *engine, int option, int64_t value);
 
 /* Matrix facts: G, C, stored non-zeros, genes per partition of the staged layout. */

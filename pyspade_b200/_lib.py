@@ -7,12 +7,12 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libspade_b200.so")
+LIB_PATH = os.environ.get("SPADE_LIB") or os.path.join(_PKG, "libspade_b200.so")   # SPADE_LIB: tuning variants
 
 SPADE_OK, SPADE_ERR_ARG, SPADE_ERR_CUDA, SPADE_ERR_STATE = 0, 1, 2, 3
 SPADE_HOST, SPADE_DEVICE = 0, 1
 SPADE_ABI_VERSION = 2
-SPADE_OPT_TAIL_TABLE, SPADE_OPT_MEMBER_BLOCK, SPADE_OPT_GENES_PER_PART = 1, 2, 3
+SPADE_OPT_TAIL_TABLE, SPADE_OPT_MEMBER_BLOCK, SPADE_OPT_GENES_PER_PART, SPADE_OPT_SORT_MEMBERS = 1, 2, 3, 4
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64p = ctypes.POINTER(ctypes.c_int64)

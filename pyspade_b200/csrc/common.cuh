@@ -22,6 +22,8 @@ constexpr int kMaxGenesPerPart = 1 << kSlotBits;      // 8192
 // A warp accumulates at most this many member cells before its accumulators are drained:
 // the 16-bit count field and the 47-bit sum budget (see stage.cuh) are sized for it.
 constexpr int kMemberBlock = 32768;
+constexpr int kSegAlign = 16;                         // entries: segments start on 128-byte lines
+constexpr int kDenseLanes = 32;                       // genes per partition kept in the dense block
 
 struct __align__(16) GeneMeta {      // one per gene, fixed by the matrix and the background
     int32_t n;                       // #{cells : x <= cutoff}             (utils.py:200,211)

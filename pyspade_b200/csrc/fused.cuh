@@ -11,9 +11,40 @@
 
 namespace spade {
 
+#ifndef SPADE_MEMBER_BATCH
+#define SPADE_MEMBER_BATCH 4
+#endif
+#ifndef SPADE_ITERS
+#define SPADE_ITERS 3
+#endif
+#ifndef SPADE_MIN_CTAS
+#define SPADE_MIN_CTAS 6
+#endif
+#ifndef SPADE_PIPELINE
+#define SPADE_PIPELINE 0
+#endif
+#ifndef SPADE_LOAD
+#define SPADE_LOAD 1
+#endif
+// Streaming 64-bit load of layout data.  The kernel keeps almost all of the SM's 228 KB as
+// shared memory, so L1 has only a few hundred lines: loads that allocate there (ld.global.nc)
+// stall once more lines are pending than exist.  ld.global.cg goes through L2 only.
+__device__ __forceinline__ unsigned long long stream_load(const unsigned long long *p)
+{
+#if SPADE_LOAD == 0
+    return __ldg(p);
+#elif SPADE_LOAD == 1
+    return __ldcg(p);
+#else
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#endif
+}
+
 constexpr int kWarpsPerCta = 4;
-constexpr int kMemberBatch = 4;   // member cells whose segments are in flight per warp
-constexpr int kIters = 3;         // unrolled 32-entry steps per member segment
+constexpr int kMemberBatch = SPADE_MEMBER_BATCH;   // member cells whose segments are in flight per warp
+constexpr int kIters = SPADE_ITERS;                // unrolled 32-entry steps per member segment
 
 struct FinCtx {
     int64_t G;
@@ -68,7 +99,9 @@ __device__ __forceinline__ void finalize_test(const FinCtx &f, int64_t row, int6
 
 struct RunArgs {
     const unsigned long long *ent;
-    const uint32_t *pptr;
+    const uint2 *seg;             // [P*C] (begin, end) of every (partition, cell) segment
+    const int32_t *dgene;         // [P*32] gene held by each lane of the dense head, -1 = none
+    const uint8_t *dense_on;      // [P] partition uses its dense block
     const int32_t *members;
     const int64_t *offsets;       // device copy of the caller's offsets
     int64_t s0;                   // first set of this launch
@@ -96,7 +129,7 @@ __device__ __forceinline__ void decode_entry(unsigned long long e, uint32_t &slo
 }
 
 template <bool kSplit>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_de_fused(const RunArgs a)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(const RunArgs a)
 {
     extern __shared__ unsigned long long smem_acc[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,63 +160,113 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_de_fused(const RunArgs a)
     for (int j = lane; j < ng; j += 32) acc[j] = 0ull;
     __syncwarp();
 
-    const uint32_t *__restrict__ pp = a.pptr + (int64_t)p * a.C;
+    const uint2 *__restrict__ seg = a.seg + (int64_t)p * a.C;
     const int32_t *__restrict__ mem = a.members + mbeg;
     const unsigned long long *__restrict__ ent = a.ent;
+    // dense head of this partition's segments: lane l accumulates the partition's l-th densest
+    // gene in a register, one aligned 256-byte read per member cell, no shared-memory traffic
+    const bool dense = a.dense_on[p] != 0;
+    const uint32_t head = dense ? kDenseLanes : 0;
+    unsigned long long dacc = 0ull;
 
-    for (int m0 = 0; m0 < cntm; m0 += 32) {
-        uint32_t b = 0, e = 0;
-        if (m0 + lane < cntm) {
-            const int32_t c = mem[m0 + lane];
+    // Software pipeline over batches of kMemberBatch member cells: the loads of batch i+1 are
+    // in flight while batch i is added into the accumulators.  Member ids and their segment
+    // bounds are fetched 32 members at a time, one group ahead (two register sets by parity).
+    uint32_t mb[2] = {0, 0}, me[2] = {0, 0};
+    auto fetch_meta = [&](int grp, uint32_t &b, uint32_t &e) {
+        b = 0; e = 0;                                  // b == e == 0: no member in this lane
+        const int m = grp * 32 + lane;
+        if (m < cntm) {
+            const int32_t c = mem[m];
             if ((uint32_t)c < (uint32_t)a.C) {
-                b = __ldg(pp + c);
-                e = __ldg(pp + c + 1);
+                const uint2 se = __ldg(seg + c);
+                b = se.x;
+                e = se.y;
             } else {
                 atomicExch(a.err, 2);
             }
         }
-        const int lim = min(32, cntm - m0);
-        for (int j = 0; j < lim; j += kMemberBatch) {
-            uint32_t bb[kMemberBatch], ee[kMemberBatch];
-            unsigned long long r[kMemberBatch][kIters];
-#pragma unroll
-            for (int q = 0; q < kMemberBatch; ++q) {
-                bb[q] = __shfl_sync(0xffffffffu, b, j + q) + lane;
-                ee[q] = __shfl_sync(0xffffffffu, e, j + q);
-            }
-#pragma unroll
-            for (int q = 0; q < kMemberBatch; ++q)
-#pragma unroll
-                for (int it = 0; it < kIters; ++it) {
-                    const uint32_t i = bb[q] + 32 * it;
-                    r[q][it] = i < ee[q] ? __ldg(ent + i) : 0ull;
-                }
-#pragma unroll
-            for (int q = 0; q < kMemberBatch; ++q) {
-                uint32_t slot[kIters];
-                unsigned long long add[kIters], cur[kIters];
-                bool ok[kIters];
-#pragma unroll
-                for (int it = 0; it < kIters; ++it) {
-                    ok[it] = bb[q] + 32 * it < ee[q];
-                    decode_entry(r[q][it], slot[it], add[it]);
-                }
-                // the genes of one cell are distinct: the loads of all steps may precede the stores
-#pragma unroll
-                for (int it = 0; it < kIters; ++it)
-                    if (ok[it]) cur[it] = acc[slot[it]];
-#pragma unroll
-                for (int it = 0; it < kIters; ++it)
-                    if (ok[it]) acc[slot[it]] = cur[it] + add[it];
-                for (uint32_t i = bb[q] + 32 * kIters; i < ee[q]; i += 32) {     // long segments
-                    uint32_t sl;
-                    unsigned long long ad;
-                    decode_entry(__ldg(ent + i), sl, ad);
-                    acc[sl] += ad;
-                }
-                __syncwarp();      // next cell may hit the same genes from other lanes
-            }
+    };
+    struct Batch {
+        uint32_t bb[kMemberBatch], ee[kMemberBatch];
+        unsigned long long r[kMemberBatch][kIters], dv[kMemberBatch];
+    };
+    constexpr int kBatchesPerGroup = 32 / kMemberBatch;
+    auto load = [&](Batch &t, int ib) {
+        const int grp = ib / kBatchesPerGroup, w = (ib % kBatchesPerGroup) * kMemberBatch;
+        if (w == 0) {                                  // entering a group: prefetch the next one
+            if (grp & 1) fetch_meta(grp + 1, mb[0], me[0]);
+            else fetch_meta(grp + 1, mb[1], me[1]);
         }
+        const uint32_t b = (grp & 1) ? mb[1] : mb[0], e = (grp & 1) ? me[1] : me[0];
+#pragma unroll
+        for (int q = 0; q < kMemberBatch; ++q) {
+            const uint32_t bq = __shfl_sync(0xffffffffu, b, w + q);
+            t.ee[q] = __shfl_sync(0xffffffffu, e, w + q);
+            t.dv[q] = (dense && t.ee[q] != 0) ? stream_load(ent + bq + lane) : 0ull;
+            t.bb[q] = bq + head + lane;
+        }
+#pragma unroll
+        for (int q = 0; q < kMemberBatch; ++q)
+#pragma unroll
+            for (int it = 0; it < kIters; ++it) {
+                const uint32_t i = t.bb[q] + 32 * it;
+                t.r[q][it] = i < t.ee[q] ? stream_load(ent + i) : 0ull;
+            }
+    };
+    auto process = [&](const Batch &t) {
+#pragma unroll
+        for (int q = 0; q < kMemberBatch; ++q) {
+            uint32_t slot[kIters];
+            unsigned long long add[kIters], cur[kIters];
+            bool ok[kIters];
+#pragma unroll
+            for (int it = 0; it < kIters; ++it) {
+                ok[it] = t.bb[q] + 32 * it < t.ee[q];
+                decode_entry(t.r[q][it], slot[it], add[it]);
+            }
+            // the genes of one cell are distinct: the loads of all steps may precede the stores
+#pragma unroll
+            for (int it = 0; it < kIters; ++it)
+                if (ok[it]) cur[it] = acc[slot[it]];
+#pragma unroll
+            for (int it = 0; it < kIters; ++it)
+                if (ok[it]) acc[slot[it]] = cur[it] + add[it];
+            for (uint32_t i = t.bb[q] + 32 * kIters; i < t.ee[q]; i += 32) {     // long segments
+                uint32_t sl;
+                unsigned long long ad;
+                decode_entry(stream_load(ent + i), sl, ad);
+                acc[sl] += ad;
+            }
+            dacc += t.dv[q];
+            __syncwarp();          // next cell may hit the same genes from other lanes
+        }
+    };
+    const int nb = (cntm + kMemberBatch - 1) / kMemberBatch;
+    if (nb > 0) {
+        fetch_meta(0, mb[0], me[0]);
+#if SPADE_PIPELINE
+        Batch A, B;
+        load(A, 0);
+        for (int ib = 0; ib < nb; ib += 2) {
+            if (ib + 1 < nb) load(B, ib + 1);
+            process(A);
+            if (ib + 1 >= nb) break;
+            if (ib + 2 < nb) load(A, ib + 2);
+            process(B);
+        }
+#else
+        Batch A;
+        for (int ib = 0; ib < nb; ++ib) {
+            load(A, ib);
+            process(A);
+        }
+#endif
+    }
+    if (dense) {                   // hand the register accumulators to the common finalize
+        const int32_t dg = a.dgene[p * kDenseLanes + lane];
+        if (dg >= 0) acc[dg - g0] = dacc;
+        __syncwarp();
     }
 
     if (!kSplit) {

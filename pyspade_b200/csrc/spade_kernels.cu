@@ -3,9 +3,13 @@
 //
 // Data layout in HBM (per engine, one engine per GPU)
 //   CSR copy of the caller's matrix      indptr int64[G+1], indices int32[nnz], values f64[nnz]
-//   gene-partitioned cell-major entries  pptr uint32[P*C+1], ent uint64[nnz]   (common.cuh)
+//   gene-partitioned cell-major entries  seg uint2[P*C] (begin, end), ent uint64[padded nnz]
 //                                          segment (p, c) = the stored values of cell c whose
-//                                          gene lies in partition p (Gp consecutive genes)
+//                                          gene lies in partition p (Gp consecutive genes);
+//                                          segments start on 128-byte lines (common.cuh)
+//                                          a partition whose 32 densest genes cover enough
+//                                          entries keeps them as a dense 32-word head of each
+//                                          segment (one word per gene, zero = not expressed)
 //   per gene                             median f64, n int32, GeneMeta {n, shift, negmode,
 //                                          rowsum | bgmean}
 //   log-factorial table                  lf f64[C+1], lf[i] = ln(i!)
@@ -43,6 +47,7 @@ constexpr int64_t kMaxTestsSplitChunk = int64_t(1) << 24;   // split mode: globa
 constexpr int64_t kMaxTableEntries = int64_t(1) << 26;      // tail table: 1 GiB of double2
 constexpr int kDefaultGenesPerPart = 1024;
 constexpr int kTargetCopyGroups = 12;                       // host outputs: strips per batch
+constexpr double kDenseMinEntries = 6.0;                    // dense block must remove >= this many entries per cell
 
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
@@ -71,12 +76,20 @@ struct spade_engine {
     int member_block = kMemberBlock;
     int gp_request = 0;                // 0 = default
     int bank_order = 1;                // lay segments out for conflict-free accumulator access
+    int dense_blocks = 1;              // register-accumulated dense block per partition
+    int sort_members = 1;              // walk every set in ascending cell order (L2 locality)
 
     DevBuf<int64_t> indptr;
     DevBuf<int32_t> indices;
     DevBuf<double> values;
-    DevBuf<uint32_t> pptr, cursor;
+    DevBuf<uint32_t> pptr, cursor;     // pptr = first entry of every segment
+    DevBuf<uint2> seg;
     DevBuf<unsigned long long> ent;
+    DevBuf<int8_t> dslot;
+    DevBuf<int32_t> dgene;
+    DevBuf<uint8_t> dense_on;
+    bool any_dense = false;
+    int64_t ent_len = 0;
     DevBuf<double> median, lf;
     DevBuf<int32_t> n;
     DevBuf<GeneMeta> meta;
@@ -85,7 +98,8 @@ struct spade_engine {
     std::vector<int32_t> h_n;
 
     // run workspace
-    DevBuf<int32_t> members;
+    DevBuf<int32_t> members, members_sorted;
+    DevBuf<uint8_t> sort_temp;
     DevBuf<int64_t> offsets;
     DevBuf<TabMeta> tmeta;
     DevBuf<double2> tab;
@@ -166,8 +180,13 @@ struct spade_engine {
     // K1 + entry scatter; re-run whenever the background changes.
     int stage_genes(cudaStream_t st)
     {
-        const size_t np = (size_t)P * (size_t)C + 1;
-        CUDA_TRY(cudaMemcpyAsync(cursor.p, pptr.p, np * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        const size_t np = (size_t)P * (size_t)C;
+        if (np > 0) {
+            k_init_cursor<<<grid_for(np, 256), 256, 0, st>>>(pptr.p, (int64_t)np, C, dense_on.p, cursor.p);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (any_dense && ent_len > 0)      // dense heads: words of genes a cell does not express stay zero
+            CUDA_TRY(cudaMemsetAsync(ent.p, 0, ent_len * sizeof(unsigned long long), st));
         StageArgs a;
         a.indptr = indptr.p;
         a.indices = indices.p;
@@ -178,6 +197,8 @@ struct spade_engine {
         a.Gp = Gp;
         a.cursor = cursor.p;
         a.ent = ent.p;
+        a.dslot = dslot.p;
+        a.begin = pptr.p;
         a.median = median.p;
         a.n = n.p;
         a.meta = meta.p;
@@ -187,7 +208,7 @@ struct spade_engine {
         if (nnz > 0 && bank_order) {
             const int64_t nseg = (int64_t)P * C;
             k_bank_order<<<(unsigned)((nseg + kOrderWarps - 1) / kOrderWarps), kOrderWarps * 32, 0, st>>>(
-                pptr.p, nseg, ent.p);
+                seg.p, nseg, C, dense_on.p, ent.p);
             CUDA_TRY(cudaGetLastError());
         }
         h_n.resize((size_t)G);
@@ -211,15 +232,18 @@ struct spade_engine {
             set_error("partition index does not fit: (G / genes_per_part) * C must stay below 4e9");
             return SPADE_ERR_ARG;
         }
-        const size_t np = (size_t)P * (size_t)C + 1;
+        const size_t np = (size_t)P * (size_t)C;
 
         CUDA_TRY(pptr.reserve(np));
         CUDA_TRY(cursor.reserve(np));
-        CUDA_TRY(ent.reserve(nnz));
+        CUDA_TRY(seg.reserve(np));
         CUDA_TRY(median.reserve(G));
         CUDA_TRY(n.reserve(G));
         CUDA_TRY(meta.reserve(G));
         CUDA_TRY(ncmask.reserve(C));
+        CUDA_TRY(dslot.reserve(G));
+        CUDA_TRY(dgene.reserve((size_t)P * kDenseLanes));
+        CUDA_TRY(dense_on.reserve(P));
 
         // log-factorial table, host lgamma (<= 1 ulp), one entry per population size
         {
@@ -233,21 +257,75 @@ struct spade_engine {
             CUDA_TRY(cudaStreamSynchronize(st));
         }
 
-        // segment sizes per (partition, cell) -> exclusive scan -> pptr
-        CUDA_TRY(cudaMemsetAsync(cursor.p, 0, np * sizeof(uint32_t), st));
-        if (G > 0 && nnz > 0) {
-            k_part_hist<<<(unsigned)G, kStageThreads, 0, st>>>(indptr.p, indices.p, C, Gp, cursor.p, err.p);
-            CUDA_TRY(cudaGetLastError());
-        }
+        // Dense block: the kDenseLanes genes of each partition with the most stored values, used
+        // when they take enough entries out of the segments to pay for the extra 256-byte read.
         {
+            std::vector<int64_t> hp(G + 1);
+            CUDA_TRY(cudaMemcpy(hp.data(), indptr.p, (G + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+            std::vector<int8_t> hslot(G, (int8_t)-1);
+            std::vector<int32_t> hgene((size_t)P * kDenseLanes, -1);
+            std::vector<uint8_t> hon(P, 0);
+            any_dense = false;
+            std::vector<int64_t> order;
+            for (int p = 0; p < P && dense_blocks; ++p) {
+                const int64_t g0 = (int64_t)p * Gp, g1 = std::min<int64_t>(G, g0 + Gp);
+                order.resize(g1 - g0);
+                for (int64_t g = g0; g < g1; ++g) order[g - g0] = g;
+                const size_t top = std::min<size_t>(kDenseLanes, order.size());
+                std::partial_sort(order.begin(), order.begin() + top, order.end(), [&](int64_t x, int64_t y) {
+                    const int64_t nx = hp[x + 1] - hp[x], ny = hp[y + 1] - hp[y];
+                    return nx != ny ? nx > ny : x < y;
+                });
+                int64_t covered = 0;
+                for (size_t i = 0; i < top; ++i) covered += hp[order[i] + 1] - hp[order[i]];
+                if (C > 0 && (double)covered / (double)C >= kDenseMinEntries) {
+                    hon[p] = 1;
+                    any_dense = true;
+                    for (size_t i = 0; i < top; ++i) {
+                        hslot[order[i]] = (int8_t)i;
+                        hgene[(size_t)p * kDenseLanes + i] = (int32_t)order[i];
+                    }
+                }
+            }
+            CUDA_TRY(cudaMemcpy(dslot.p, hslot.data(), G * sizeof(int8_t), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(dgene.p, hgene.data(), hgene.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(dense_on.p, hon.data(), P * sizeof(uint8_t), cudaMemcpyHostToDevice));
+        }
+
+        // segment sizes per (partition, cell) -> padded to 128-byte lines -> exclusive scan
+        ent_len = 0;
+        if (np > 0) {
+            DevBuf<uint32_t> count;
+            CUDA_TRY(count.reserve(np));
+            CUDA_TRY(cudaMemsetAsync(count.p, 0, np * sizeof(uint32_t), st));
+            if (G > 0 && nnz > 0) {
+                k_part_hist<<<(unsigned)G, kStageThreads, 0, st>>>(indptr.p, indices.p, C, Gp, dslot.p, count.p, err.p);
+                CUDA_TRY(cudaGetLastError());
+            }
+            k_pad_counts<<<grid_for(np, 256), 256, 0, st>>>(count.p, (int64_t)np, C, dense_on.p, cursor.p);
+            CUDA_TRY(cudaGetLastError());
             size_t scan_bytes = 0;
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cursor.p, pptr.p, (int64_t)np, st));
             DevBuf<uint8_t> temp;
             CUDA_TRY(temp.reserve(scan_bytes));
+            // padded total <= nnz + (dense head + 15) per segment: must fit the 32-bit entry index
+            if ((unsigned long long)nnz + (unsigned long long)(kSegAlign - 1 + (any_dense ? kDenseLanes : 0)) * np >
+                0xffff0000ull) {
+                set_error("matrix too large: padded entry count must stay below 2^32 - 65536");
+                return SPADE_ERR_ARG;
+            }
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp.p, scan_bytes, cursor.p, pptr.p, (int64_t)np, st));
+            k_make_segments<<<grid_for(np, 256), 256, 0, st>>>(pptr.p, count.p, (int64_t)np, C, dense_on.p, seg.p);
+            CUDA_TRY(cudaGetLastError());
+            uint32_t last_begin = 0, last_pad = 0;
+            CUDA_TRY(cudaMemcpyAsync(&last_begin, pptr.p + (np - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(&last_pad, cursor.p + (np - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
+            ent_len = (int64_t)last_begin + (int64_t)last_pad;
             temp.release();
+            count.release();
         }
+        CUDA_TRY(ent.reserve(ent_len));
         int rc = check_device_error("spade_create");
         if (rc != SPADE_OK) return rc;
 
@@ -350,8 +428,10 @@ struct spade_engine {
     void free_all()
     {
         indptr.release(); indices.release(); values.release(); pptr.release(); cursor.release();
+        seg.release(); dslot.release(); dgene.release(); dense_on.release();
         ent.release(); median.release(); lf.release(); n.release(); meta.release(); ncmask.release();
-        err.release(); members.release(); offsets.release(); tmeta.release(); tab.release();
+        err.release(); members.release(); members_sorted.release(); sort_temp.release();
+        offsets.release(); tmeta.release(); tab.release();
         blk_row.release(); blk_cnt.release(); blk_off.release(); gsum.release(); gcnt.release();
         for (int b = 0; b < 4; ++b) out_f64[b].release();
         out_k.release();
@@ -396,6 +476,7 @@ int create_common(int device, int64_t G, int64_t C, const int64_t *indptr, const
     e->C = C;
     if (const char *gp = getenv("SPADE_GENES_PER_PART")) e->gp_request = atoi(gp);
     if (const char *bo = getenv("SPADE_BANK_ORDER")) e->bank_order = atoi(bo) != 0;
+    if (const char *db = getenv("SPADE_DENSE_BLOCKS")) e->dense_blocks = atoi(db) != 0;
     auto bail = [&](int code) {
         g_create_error = e->error;
         e->free_all();
@@ -529,6 +610,9 @@ int spade_set_option(spade_engine *engine, int option, int64_t value)
         if (value < 1 || value > kMemberBlock) { set_error("member block must be in [1, 32768]"); return SPADE_ERR_ARG; }
         engine->member_block = (int)value;
         return SPADE_OK;
+    case SPADE_OPT_SORT_MEMBERS:
+        engine->sort_members = value != 0;
+        return SPADE_OK;
     case SPADE_OPT_GENES_PER_PART:
         if (value < 0 || value > 4096) { set_error("genes per partition must be in [0, 4096]"); return SPADE_ERR_ARG; }
         CUDA_TRY(cudaDeviceSynchronize());
@@ -600,6 +684,21 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
     CUDA_TRY(engine->offsets.reserve(S + 1));
     CUDA_TRY(cudaMemcpyAsync(engine->offsets.p, offsets, (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
 
+    // Member cells of every set in ascending order: the warps working on one gene partition
+    // then sweep the cells in step, so a segment fetched for one set is still in L2 when the
+    // other sets that contain the cell ask for it.  Order inside a set does not change any sum.
+    if (engine->sort_members && total > 1) {
+        CUDA_TRY(engine->members_sorted.reserve(total));
+        size_t tb = 0;
+        CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(nullptr, tb, d_members, engine->members_sorted.p, total, S,
+                                                    engine->offsets.p, engine->offsets.p + 1, st));
+        CUDA_TRY(engine->sort_temp.reserve(tb));
+        CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(engine->sort_temp.p, tb, d_members, engine->members_sorted.p,
+                                                    total, S, engine->offsets.p, engine->offsets.p + 1, st));
+        d_members = engine->members_sorted.p;
+        engine->launches += 1;
+    }
+
     const bool host_out = out_location == SPADE_HOST;
     double *outs[4] = {up, down, fc, cpm};
     if (host_out) {
@@ -637,7 +736,9 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
         RunArgs a;
         memset(&a, 0, sizeof(a));
         a.ent = engine->ent.p;
-        a.pptr = engine->pptr.p;
+        a.seg = engine->seg.p;
+        a.dgene = engine->dgene.p;
+        a.dense_on = engine->dense_on.p;
         a.members = d_members;
         a.offsets = engine->offsets.p;
         a.s0 = s0;

@@ -43,15 +43,53 @@ __global__ void k_cpm(const int32_t *__restrict__ indices, const int32_t *__rest
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kStageThreads)
 k_part_hist(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, int64_t C,
-            int Gp, uint32_t *__restrict__ hist, int *__restrict__ err)
+            int Gp, const int8_t *__restrict__ dslot, uint32_t *__restrict__ hist,
+            int *__restrict__ err)
 {
     const int64_t g = blockIdx.x;
     const int64_t base = (g / Gp) * C;
+    const bool dense = dslot[g] >= 0;             // lives in the dense block, not in a segment
     for (int64_t i = indptr[g] + threadIdx.x; i < indptr[g + 1]; i += blockDim.x) {
         const int32_t c = indices[i];
         if (c < 0 || c >= C) { atomicExch(err, 1); continue; }
-        atomicAdd(&hist[base + c], 1u);
+        if (!dense) atomicAdd(&hist[base + c], 1u);
     }
+}
+
+// Segments start on 128-byte boundaries (16 entries): a warp's 256-byte read of 32 entries
+// then touches two lines instead of three.  A partition with a dense block keeps it at the
+// head of every segment: kDenseLanes words, word l = the partition's l-th densest gene in this
+// cell (zero = not expressed), then the packed entries of the other genes.
+// padded[i] = (dense head + count[i]) rounded up to 16.
+__global__ void k_pad_counts(const uint32_t *__restrict__ count, int64_t n, int64_t C,
+                             const uint8_t *__restrict__ dense_on, uint32_t *__restrict__ padded)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t head = dense_on[i / C] ? kDenseLanes : 0;
+        padded[i] = (head + count[i] + (kSegAlign - 1)) & ~(uint32_t)(kSegAlign - 1);
+    }
+}
+
+// seg[i] = (first word of the segment, one past its last packed entry)
+__global__ void k_make_segments(const uint32_t *__restrict__ begin, const uint32_t *__restrict__ count,
+                                int64_t n, int64_t C, const uint8_t *__restrict__ dense_on,
+                                uint2 *__restrict__ seg)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t head = dense_on[i / C] ? kDenseLanes : 0;
+        seg[i] = make_uint2(begin[i], begin[i] + head + count[i]);
+    }
+}
+
+// cursor[i] = first packed entry of the segment (after the dense head)
+__global__ void k_init_cursor(const uint32_t *__restrict__ begin, int64_t n, int64_t C,
+                              const uint8_t *__restrict__ dense_on, uint32_t *__restrict__ cursor)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        cursor[i] = begin[i] + (dense_on[i / C] ? kDenseLanes : 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -84,6 +122,8 @@ struct StageArgs {
     int Gp;
     uint32_t *cursor;         // running write position of every (partition, cell) segment
     unsigned long long *ent;
+    const int8_t *dslot;      // per gene: lane of the dense block, or -1
+    const uint32_t *begin;    // first word of every (partition, cell) segment
     double *median;
     int32_t *n;
     GeneMeta *meta;
@@ -189,6 +229,7 @@ __global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
     const int64_t part = g / a.Gp;
     const unsigned long long slot = (unsigned long long)(g - part * a.Gp) << kFieldBits;
     uint32_t *cursor = a.cursor + part * a.C;
+    const int ds = a.dslot[g];
     long long n_low = 0, rowsum = 0, bgsum = 0;
     for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
         const double v = a.values[i];
@@ -201,8 +242,13 @@ __global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
         const long long flag = negmode ? (low ? 1 : 0) : (low ? 0 : 1);
         const unsigned long long field =
             (unsigned long long)((flag << kCountShift) + fx) & ((1ull << kFieldBits) - 1);
-        const uint32_t at = atomicAdd(&cursor[c], 1u);
-        a.ent[at] = slot | field;
+        if (ds >= 0) {
+            // dense gene: the sign-extended field itself, one 64-bit word per (cell, lane)
+            a.ent[a.begin[part * a.C + c] + ds] = (unsigned long long)((flag << kCountShift) + fx);
+        } else {
+            const uint32_t at = atomicAdd(&cursor[c], 1u);
+            a.ent[at] = slot | field;
+        }
     }
     n_low = block_sum(n_low, scratch_ll);
     rowsum = block_sum(rowsum, scratch_ll);
@@ -237,14 +283,15 @@ constexpr int kOrderChunk = 512;
 constexpr int kOrderWarps = 8;
 
 __global__ void __launch_bounds__(kOrderWarps * 32)
-k_bank_order(const uint32_t *__restrict__ pptr, int64_t nseg, unsigned long long *__restrict__ ent)
+k_bank_order(const uint2 *__restrict__ segs, int64_t nseg, int64_t C, const uint8_t *__restrict__ dense_on,
+             unsigned long long *__restrict__ ent)
 {
     __shared__ unsigned long long buf[kOrderWarps][kOrderChunk];
     __shared__ int bins[kOrderWarps][16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t seg = blockIdx.x * (int64_t)kOrderWarps + warp;
     if (seg >= nseg) return;
-    const uint32_t beg = pptr[seg], end = pptr[seg + 1];
+    const uint32_t beg = segs[seg].x + (dense_on[seg / C] ? kDenseLanes : 0), end = segs[seg].y;
     for (uint32_t c0 = beg; c0 < end; c0 += kOrderChunk) {
         const int m = (int)min((uint32_t)kOrderChunk, end - c0);
         if (m <= 16) break;                                  // a single row: nothing to gain

@@ -149,7 +149,8 @@ class Engine:
         (cells per warp before draining; larger sets take the split path),
         ``genes_per_part`` (re-stages the layout).  See ``spade_set_option``."""
         opt = {"tail_table": _lib.SPADE_OPT_TAIL_TABLE, "member_block": _lib.SPADE_OPT_MEMBER_BLOCK,
-               "genes_per_part": _lib.SPADE_OPT_GENES_PER_PART}[name]
+               "genes_per_part": _lib.SPADE_OPT_GENES_PER_PART,
+               "sort_members": _lib.SPADE_OPT_SORT_MEMBERS}[name]
         self._check(self._lib.spade_set_option(self._h, opt, int(value)))
         if name == "genes_per_part":
             f = ctypes.c_int32()

@@ -314,3 +314,35 @@ def test_non_finite_values_are_refused():
     X = sp.csr_matrix(np.array([[1.0, np.inf, 0.0], [0.0, 2.0, 3.0]]))
     with pytest.raises(SpadeError):
         Engine.from_cpm(X)
+
+
+def test_layout_switches_do_not_change_results(monkeypatch):
+    """Dense blocks (register accumulation of each partition's densest genes) and the
+    bank-aware segment order are pure layout choices: tables are bit-identical without them."""
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 2300, 1800
+    counts = synth.counts_numpy(G, C, seed=17)
+    sets = synth.deobs_sets(C, 9, lo=5, hi=1200) + synth.derand_draws(C, 77, 5)
+    nc = np.arange(1, C, 13)
+    res = {}
+    for dense, order in ((1, 1), (0, 1), (1, 0), (0, 0)):
+        monkeypatch.setenv("SPADE_DENSE_BLOCKS", str(dense))
+        monkeypatch.setenv("SPADE_BANK_ORDER", str(order))
+        with Engine.from_counts(counts) as eng:
+            a = eng.run(sets, want_k=True)
+            eng.set_background(nc)
+            b = eng.run(sets, want_k=True)
+        res[(dense, order)] = (a, b)
+    with Engine.from_counts(counts) as eng:
+        eng.set_option("sort_members", 0)               # caller's member order
+        res["unsorted"] = (eng.run(sets, want_k=True), None)
+        eng.set_background(nc)
+        res["unsorted"] = (res["unsorted"][0], eng.run(sets, want_k=True))
+    for key in res:
+        _tables_equal(res[(1, 1)][0], res[key][0])
+        _tables_equal(res[(1, 1)][1], res[key][1])
+    X = de_port.cpm_normalization_port(counts)
+    ora = de_port.de_tables(X, sets, nc, tail_fn=c_oracle.hypergeom_logcdf_logsf)
+    assert np.array_equal(res[(1, 1)][1]["k"], ora["k"])
+    assert_tables_close(res[(1, 1)][1], ora)

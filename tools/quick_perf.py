@@ -14,6 +14,7 @@ ap.add_argument("--C", type=int, default=50000)
 ap.add_argument("--N", type=int, default=500)
 ap.add_argument("--S", type=int, default=200)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--sort", action="store_true")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -25,6 +26,8 @@ t0 = time.time()
 eng = Engine.from_device_csr(a.G, a.C, indptr, indices, counts, device=0)
 print(f"stage {time.time()-t0:.2f}s genes_per_part={eng.genes_per_part}")
 draws = synth.derand_draws(a.C, a.N, a.S)
+if a.sort:
+    draws = [np.sort(d) for d in draws]
 members, offsets = synth.concat_sets(draws)
 dm = torch.from_numpy(members).to(dev)
 out = {k: torch.empty((a.S, a.G), dtype=torch.float64, device=dev) for k in ("up", "down", "cpm", "fc")}
