@@ -118,6 +118,52 @@ struct DevBuf {
     }
 };
 
+// Page-locked staging buffer for small host->device uploads issued on a stream: a copy from
+// pageable memory would synchronise the stream first.  `wait()` before refilling.
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+    cudaError_t reserve(size_t count)
+    {
+        cudaError_t e = wait();
+        if (e != cudaSuccess) return e;
+        if (count <= cap && p) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        e = cudaHostAlloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = std::max<size_t>(count, 1);
+        if (e == cudaSuccess && !done) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+        return e;
+    }
+    cudaError_t wait()
+    {
+        if (!pending) return cudaSuccess;
+        pending = false;
+        return cudaEventSynchronize(done);
+    }
+    cudaError_t upload(T *dst, size_t count, cudaStream_t st)
+    {
+        cudaError_t e = cudaMemcpyAsync(dst, p, count * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        pending = true;
+        return cudaEventRecord(done, st);
+    }
+    void release()
+    {
+        if (pending) cudaEventSynchronize(done);
+        pending = false;
+        if (p) cudaFreeHost(p);
+        if (done) cudaEventDestroy(done);
+        p = nullptr;
+        done = nullptr;
+        cap = 0;
+    }
+};
+
 inline int grid_for(int64_t n, int threads, int cap = 148 * 32)
 {
     int64_t b = (n + threads - 1) / threads;

@@ -112,7 +112,8 @@ struct spade_engine {
     cudaStream_t work[2] = {nullptr, nullptr}, copy_stream = nullptr;
     cudaEvent_t ev_ready = nullptr;
     std::vector<cudaEvent_t> sync_events;
-    std::vector<TabMeta> h_tmeta;
+    PinnedBuf<TabMeta> h_tmeta;
+    PinnedBuf<int64_t> h_offsets;
 
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> ev_pool;
@@ -364,7 +365,7 @@ struct spade_engine {
     int build_tail_table(int64_t N, cudaStream_t st, bool *built)
     {
         *built = false;
-        h_tmeta.resize((size_t)G);
+        CUDA_TRY(h_tmeta.reserve((size_t)G));
         const double M = (double)C;
         unsigned long long total = 0;
         for (int64_t g = 0; g < G; ++g) {
@@ -386,13 +387,13 @@ struct spade_engine {
                     t.len = (int32_t)(hi - lo + 1);
                 }
             }
-            h_tmeta[g] = t;
+            h_tmeta.p[g] = t;
             total += (unsigned long long)t.len;
         }
         if (total > (unsigned long long)kMaxTableEntries) return SPADE_OK;
         CUDA_TRY(tmeta.reserve(G));
         CUDA_TRY(tab.reserve(total));
-        CUDA_TRY(cudaMemcpyAsync(tmeta.p, h_tmeta.data(), G * sizeof(TabMeta), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h_tmeta.upload(tmeta.p, (size_t)G, st));
         int rc = span_begin(st, 1);
         if (rc != SPADE_OK) return rc;
         const int64_t threads = G * 32;
@@ -435,6 +436,8 @@ struct spade_engine {
         blk_row.release(); blk_cnt.release(); blk_off.release(); gsum.release(); gcnt.release();
         for (int b = 0; b < 4; ++b) out_f64[b].release();
         out_k.release();
+        h_tmeta.release();
+        h_offsets.release();
         for (int i = 0; i < 2; ++i) {
             if (work[i]) cudaStreamDestroy(work[i]);
             work[i] = nullptr;
@@ -682,7 +685,9 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
         d_members = engine->members.p;
     }
     CUDA_TRY(engine->offsets.reserve(S + 1));
-    CUDA_TRY(cudaMemcpyAsync(engine->offsets.p, offsets, (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(engine->h_offsets.reserve(S + 1));
+    memcpy(engine->h_offsets.p, offsets, (S + 1) * sizeof(int64_t));
+    CUDA_TRY(engine->h_offsets.upload(engine->offsets.p, (size_t)(S + 1), st));
 
     // Member cells of every set in ascending order: the warps working on one gene partition
     // then sweep the cells in step, so a segment fetched for one set is still in L2 when the

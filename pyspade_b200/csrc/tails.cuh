@@ -13,10 +13,42 @@ __device__ __forceinline__ double ln_choose(const double *__restrict__ lf, int a
     return lf[a] - lf[b] - lf[a - b];
 }
 
+// Sum of a tail relative to its edge term: 1 + r1 + r1 r2 + ... with r_i = (fa fb)/(fc fd),
+// the four factors stepping by one per term (fa, fb down; fc, fd up), until a factor reaches
+// zero (end of the support) or a term drops below kTailEps of the sum.  Division-free: with
+// P_i = prod(fa fb), D_i = prod(fc fd) the sum is N_i / D_i, N_i = N_{i-1} fc fd + P_i; the
+// three running values are rescaled by a power of two every 8 terms (factors are < 2^31, so
+// eight steps grow them by less than 2^500).
+__device__ __forceinline__ double tail_series(double fa, double fb, double fc, double fd)
+{
+    double P = 1.0, D = 1.0, Nn = 1.0;
+    bool more = fa > 0.0 && fb > 0.0;
+    while (more) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (more) {
+                const double b = fc * fd;
+                P *= fa * fb;
+                D *= b;
+                Nn = fma(Nn, b, P);
+                fa -= 1.0; fb -= 1.0; fc += 1.0; fd += 1.0;
+                more = fa > 0.0 && fb > 0.0 && !(P < Nn * kTailEps);
+            }
+        }
+        // exact power-of-two rescale that brings D into [1, 2)
+        const int e = (int)((__double2hiint(D) >> 20) & 0x7ff) - 1023;
+        const double sc = __hiloint2double((1023 - e) << 20, 0);
+        P *= sc;
+        D *= sc;
+        Nn *= sc;
+    }
+    return Nn / D;
+}
+
 // logcdf = ln P(X <= k), logsf = ln P(X > k), X ~ Hypergeom(M, n, N).
-// The tail on the far side of the mean is summed directly as pmf(edge) * (1 + r + r r' + ...),
-// the ratio recurrence in float64 anchored at a log-factorial-table log pmf; the near side is
-// log1p(-exp(far side)) - the branch rule of scipy, so values next to 0 keep their precision.
+// The tail on the far side of the mean is summed directly as pmf(edge) * tail_series, anchored
+// at a log-factorial-table log pmf; the near side is log1p(-exp(far side)) - the branch rule
+// of scipy, so values next to 0 keep their precision.
 __device__ void hyper_tails(int k, int M, int n, int N, const double *__restrict__ lf,
                             double &logcdf, double &logsf)
 {
@@ -25,31 +57,18 @@ __device__ void hyper_tails(int k, int M, int n, int N, const double *__restrict
     if (k < a)  { logcdf = -INFINITY; logsf = 0.0; return; }
     const double ln_total = ln_choose(lf, M, N);
     const bool upper_small = ((double)k + 0.5) * ((double)M + 0.5) > ((double)n - 0.5) * ((double)N - 0.5);
-    double t = 1.0, sum = 1.0;
     if (upper_small) {
         const int j = k + 1;
         const double lp = ln_choose(lf, n, j) + ln_choose(lf, M - n, N - j) - ln_total;
-        double fa = (double)(n - j), fb = (double)(N - j), fc = (double)(j + 1),
-               fd = (double)(M - n - N + j + 1);
-        while (fa > 0.0 && fb > 0.0) {
-            t *= (fa * fb) / (fc * fd);
-            sum += t;
-            if (t < sum * kTailEps) break;
-            fa -= 1.0; fb -= 1.0; fc += 1.0; fd += 1.0;
-        }
+        const double sum = tail_series((double)(n - j), (double)(N - j), (double)(j + 1),
+                                       (double)(M - n - N + j + 1));
         logsf = lp + log(sum);
         logcdf = log1p(-exp(logsf));
     } else {
         const int j = k;
         const double lp = ln_choose(lf, n, j) + ln_choose(lf, M - n, N - j) - ln_total;
-        double fa = (double)j, fb = (double)(M - n - N + j), fc = (double)(n - j + 1),
-               fd = (double)(N - j + 1);
-        while (fa > 0.0 && fb > 0.0) {
-            t *= (fa * fb) / (fc * fd);
-            sum += t;
-            if (t < sum * kTailEps) break;
-            fa -= 1.0; fb -= 1.0; fc += 1.0; fd += 1.0;
-        }
+        const double sum = tail_series((double)j, (double)(M - n - N + j), (double)(n - j + 1),
+                                       (double)(N - j + 1));
         logcdf = lp + log(sum);
         logsf = log1p(-exp(logcdf));
     }

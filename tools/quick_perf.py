@@ -15,6 +15,7 @@ ap.add_argument("--N", type=int, default=500)
 ap.add_argument("--S", type=int, default=200)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--sort", action="store_true")
+ap.add_argument("--deobs", action="store_true", help="ragged region sizes 50..2000 instead of draws")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -25,7 +26,7 @@ print(f"synth {time.time()-t0:.2f}s nnz={indices.numel()} density={indices.numel
 t0 = time.time()
 eng = Engine.from_device_csr(a.G, a.C, indptr, indices, counts, device=0)
 print(f"stage {time.time()-t0:.2f}s genes_per_part={eng.genes_per_part}")
-draws = synth.derand_draws(a.C, a.N, a.S)
+draws = synth.deobs_sets(a.C, a.S) if a.deobs else synth.derand_draws(a.C, a.N, a.S)
 if a.sort:
     draws = [np.sort(d) for d in draws]
 members, offsets = synth.concat_sets(draws)
