@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the per-rank tables reach rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -261,9 +263,34 @@ def main():
 
     out_dev = {k: torch.empty((S, G), dtype=torch.float64, device=dev) for k in TABLES}
     gathered = None
-    if world > 1 and rank == 0:
-        gathered = {k: [torch.empty((S, G), dtype=torch.float64, device=dev) for _ in range(world)]
-                    for k in TABLES}
+    peer = None
+    gather_mode = "none"
+    if world > 1:
+        # Preferred: rank 0's [S*world, G] tables mapped into every rank (CUDA IPC); each rank's
+        # test kernel stores its rows (set i of rank r = row i*world + r) straight into rank 0's
+        # HBM over NVLink.  Fallback: one NCCL gather per table.
+        from pyspade_b200 import shard
+        ok = torch.ones(1, device=dev)
+        if args.gather == "p2p":
+            try:
+                peer = shard.PeerTables(TABLES, S * world, G, rank, world, local_rank)
+            except Exception as exc:                                   # noqa: BLE001
+                print(f"[rank {rank}] peer tables unavailable: {exc}", file=sys.stderr)
+                ok.zero_()
+        else:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) > 0:
+            gather_mode = "p2p stores into rank 0 from inside the test kernel (CUDA IPC over NVLink)"
+        else:
+            if peer is not None:
+                peer.close()
+                peer = None
+            gather_mode = "nccl gather of up/down/cpm tables to rank 0"
+            if rank == 0:
+                gathered = {k: [torch.empty((S, G), dtype=torch.float64, device=dev) for _ in range(world)]
+                            for k in TABLES}
+    step_flag = torch.zeros(1, device=dev)
 
     def gather_tables():
         if world == 1:
@@ -273,11 +300,31 @@ def main():
 
     def step_device(i):
         _, _, offsets, dmem = batches[i % n_batches]
-        eng.run_device(dmem, offsets, out_dev)
-        gather_tables()
+        if peer is not None:
+            eng.run_device(dmem, offsets, {k: peer.address(k, first_row=rank) for k in TABLES},
+                           row_stride=world * G)
+            dist.all_reduce(step_flag)          # rank 0 passes this point once every rank's rows landed
+        else:
+            eng.run_device(dmem, offsets, out_dev)
+            gather_tables()
+
+    # N > 1: host tables shared by the ranks of the node (/dev/shm, page-locked in every rank);
+    # each GPU delivers its rows over its own PCIe link, rank 0 reads the same mapping
+    shared = None
+    e2e_mode = "Engine.run into pinned host tables"
+    if world > 1:
+        from pyspade_b200 import shard
+        try:
+            shared = shard.SharedHostTables(TABLES, S * world, G, rank, world)
+            e2e_mode = ("Engine.run on every rank into host tables shared by the node "
+                        "(POSIX shm, page-locked; rows interleaved by rank)")
+        except Exception as exc:                                       # noqa: BLE001
+            print(f"[rank {rank}] shared host tables unavailable: {exc}", file=sys.stderr)
+            e2e_mode = "device tables gathered to rank 0, rank 0 copies them to pinned host memory"
+    shared_out = ({k: shared.rows_view(k, rank, world, S) for k in TABLES} if shared is not None else None)
 
     # pinned host tables for the end-to-end leg (rank 0 receives every rank's tables)
-    host_rows = S * world if rank == 0 else S
+    host_rows = S * world if (rank == 0 and shared is None) else S
     pinned = {k: PinnedArray((host_rows, G), np.float64) for k in TABLES}
     host_out = {k: pinned[k].array for k in TABLES}
     host_out_t = {k: torch.from_numpy(host_out[k]) for k in TABLES}
@@ -287,13 +334,27 @@ def main():
         if world == 1:
             eng.run(members=members, offsets=offsets, out=host_out, validate=False, tables=TABLES)
             return
+        if shared is not None:
+            eng.run(members=members, offsets=offsets, out=shared_out, validate=False, tables=TABLES,
+                    row_stride=world * G)
+            dist.all_reduce(step_flag)              # every rank's rows are in the shared tables
+            torch.cuda.synchronize()
+            return
         dmem = torch.from_numpy(members).to(dev, non_blocking=True)          # H2D of the index lists
-        eng.run_device(dmem, offsets, out_dev)
-        gather_tables()
-        if rank == 0:
-            for k in TABLES:
-                for r in range(world):
-                    host_out_t[k][r * S:(r + 1) * S].copy_(gathered[k][r], non_blocking=True)
+        if peer is not None:
+            eng.run_device(dmem, offsets, {k: peer.address(k, first_row=rank) for k in TABLES},
+                           row_stride=world * G)
+            dist.all_reduce(step_flag)
+            if rank == 0:
+                for k in TABLES:
+                    host_out_t[k].copy_(peer.tensor(k), non_blocking=True)
+        else:
+            eng.run_device(dmem, offsets, out_dev)
+            gather_tables()
+            if rank == 0:
+                for k in TABLES:
+                    for r in range(world):
+                        host_out_t[k][r * S:(r + 1) * S].copy_(gathered[k][r], non_blocking=True)
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
@@ -363,9 +424,10 @@ def main():
                                        f"(BASELINE.json configs[2], complement background)",
                            "cells": C, "genes": G, "draws_per_gpu": S, "set_size": N, "nnz": nnz,
                            "density": rho, "sharding": f"draws round-robin over {world} rank(s), matrix replicated",
+                           "gather": gather_mode,
                            "l2": "inputs larger than L2: 1.0 GB cell-major matrix read + 0.8 GB of tables written per step",
                            "stage_seconds": stage_s},
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "path": e2e_mode,
                         "h2d_bytes_per_step": int(world * (4 * S * N + 8 * (S + 1))),
                         "d2h_bytes_per_step": int(world * S * G * B_OUT)},
                 "gpu_launches": int(kt["launches"]),
@@ -400,10 +462,29 @@ def main():
                                 "sample": f"{X.shape[0]} density-stratified genes x {len(sets)} draws of "
                                           f"{N} cells at full C={C} ({dt:.1f} s)"}
         line["parity"] = parity
+    # N > 1: rank 0 recomputes a few sets of another rank and compares them bit for bit with the
+    # rows that rank stored into rank 0's tables
+    if world > 1 and peer is not None:
+        step_device(0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            other = world - 1
+            theirs = all_draws[other: S * world: world][:4]
+            m2, o2 = synth.concat_sets(theirs)
+            chk = {k: torch.empty((4, G), dtype=torch.float64, device=dev) for k in TABLES}
+            eng.run_device(torch.from_numpy(m2).to(dev), o2, chk)
+            torch.cuda.synchronize()
+            same = all(bool(torch.equal(chk[k].view(torch.int64),
+                                        peer.tensor(k)[other::world][:4].view(torch.int64))) for k in TABLES)
+            line["multi_gpu_check"] = {"rows_of_rank": other, "sets": 4, "bit_identical": same}
+        dist.barrier()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 

@@ -145,6 +145,34 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
               const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
               int32_t *k, int out_location, void *stream);
 
+/*
+ * spade_run with an explicit row stride of the result tables (elements between the rows of
+ * consecutive sets; spade_run uses G).  With out_row_stride = P*G and table pointers offset
+ * by rank*G, P ranks interleave their rows (set i of rank r = row i*P + r) in ONE table:
+ *   - device outputs: a table that lives in another GPU's memory and was opened with
+ *     spade_ipc_open - the test kernel then stores its results straight into the destination
+ *     GPU over NVLink while it computes (gather fused into the kernel, no separate collective);
+ *   - host outputs: a table in host memory shared by the ranks of the node (one process per
+ *     GPU, e.g. a POSIX shared-memory mapping registered with spade_host_register) - every
+ *     GPU delivers its rows over its own PCIe link.
+ */
+int spade_run_strided(spade_engine *engine, const int32_t *members, int members_location,
+                      const int64_t *offsets, int64_t S, double *up, double *down, double *fc,
+                      double *cpm, int32_t *k, int out_location, int64_t out_row_stride,
+                      void *stream);
+
+/*
+ * Plain device memory that can be shared between the processes of one node (one process per
+ * GPU): the owner allocates and exports a 64-byte handle, peers open it and get a device
+ * pointer valid in their own process (peer access over NVLink / NVSwitch).  Thin wrappers of
+ * cudaMalloc / cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle.
+ */
+int spade_device_alloc(int device, void **dptr, int64_t bytes);
+int spade_device_free(int device, void *dptr);
+int spade_ipc_export(int device, void *dptr, unsigned char handle[64]);
+int spade_ipc_open(int device, const unsigned char handle[64], void **dptr);
+int spade_ipc_close(int device, void *dptr);
+
 /* Kernel-time accounting (CUDA events on the launch streams, accumulated since the last
  * reset).  test_ms = the fused test kernel (member accumulation + tails + table writes;
  * plus the split-path finalize), table_ms = tail-table builds.  Synchronises.
@@ -164,6 +192,9 @@ int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_
 /* Page-locked host memory for result tables (fast device->host copies). */
 int spade_host_alloc(void **ptr, int64_t bytes);
 int spade_host_free(void *ptr);
+/* Page-lock an existing host range (e.g. a shared-memory mapping) for fast copies. */
+int spade_host_register(void *ptr, int64_t bytes);
+int spade_host_unregister(void *ptr);
 
 #ifdef __cplusplus
 }

@@ -37,12 +37,23 @@ SIGNATURES = {
     "spade_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "spade_run_strided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                         ctypes.c_void_p]),
+    "spade_device_alloc": (ctypes.c_int, [ctypes.c_int, c_vpp, ctypes.c_int64]),
+    "spade_device_free": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
+    "spade_ipc_export": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p]),
+    "spade_ipc_open": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, c_vpp]),
+    "spade_ipc_close": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "spade_timing": (ctypes.c_int, [ctypes.c_void_p, c_f64p, c_f64p, c_i64p, ctypes.c_int]),
     "spade_hypergeom": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                        ctypes.c_void_p]),
     "spade_host_alloc": (ctypes.c_int, [c_vpp, ctypes.c_int64]),
     "spade_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "spade_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
+    "spade_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
 }
 
 _lib = None

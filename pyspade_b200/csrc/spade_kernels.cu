@@ -654,9 +654,9 @@ int spade_cpm_values(spade_engine *engine, double *values)
     return SPADE_OK;
 }
 
-int spade_run(spade_engine *engine, const int32_t *members, int members_location,
-              const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
-              int32_t *k, int out_location, void *stream)
+static int run_impl(spade_engine *engine, const int32_t *members, int members_location,
+                    const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
+                    int32_t *k, int out_location, int64_t out_row_stride, void *stream)
 {
     if (!engine) return SPADE_ERR_ARG;
     CUDA_TRY(cudaSetDevice(engine->device));
@@ -758,7 +758,7 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
         a.fin.tmeta = table ? engine->tmeta.p : nullptr;
         a.fin.tab = table ? engine->tab.p : nullptr;
         a.fin.lf = engine->lf.p;
-        a.fin.ld = G;
+        a.fin.ld = host_out ? G : out_row_stride;
         if (host_out) {
             for (int t = 0; t < 4; ++t)
                 if (outs[t]) CUDA_TRY(engine->out_f64[t].reserve(Sb * G));
@@ -769,11 +769,11 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
             a.fin.cpm = cpm ? engine->out_f64[3].p : nullptr;
             a.fin.k = k ? engine->out_k.p : nullptr;
         } else {
-            a.fin.up = up ? up + s0 * G : nullptr;
-            a.fin.down = down ? down + s0 * G : nullptr;
-            a.fin.fc = fc ? fc + s0 * G : nullptr;
-            a.fin.cpm = cpm ? cpm + s0 * G : nullptr;
-            a.fin.k = k ? k + s0 * G : nullptr;
+            a.fin.up = up ? up + s0 * out_row_stride : nullptr;
+            a.fin.down = down ? down + s0 * out_row_stride : nullptr;
+            a.fin.fc = fc ? fc + s0 * out_row_stride : nullptr;
+            a.fin.cpm = cpm ? cpm + s0 * out_row_stride : nullptr;
+            a.fin.k = k ? k + s0 * out_row_stride : nullptr;
         }
 
         if (split) {
@@ -817,11 +817,15 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
             engine->launches += 1;
             CUDA_TRY(cudaStreamSynchronize(st));     // the host vectors above go out of scope
             if (host_out) {
-                const size_t fb = Sb * G * sizeof(double);
                 for (int t = 0; t < 4; ++t)
                     if (outs[t])
-                        CUDA_TRY(cudaMemcpyAsync(outs[t] + s0 * G, engine->out_f64[t].p, fb, cudaMemcpyDeviceToHost, st));
-                if (k) CUDA_TRY(cudaMemcpyAsync(k + s0 * G, engine->out_k.p, Sb * G * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                        CUDA_TRY(cudaMemcpy2DAsync(outs[t] + s0 * out_row_stride, out_row_stride * sizeof(double),
+                                                   engine->out_f64[t].p, G * sizeof(double), G * sizeof(double),
+                                                   Sb, cudaMemcpyDeviceToHost, st));
+                if (k)
+                    CUDA_TRY(cudaMemcpy2DAsync(k + s0 * out_row_stride, out_row_stride * sizeof(int32_t),
+                                               engine->out_k.p, G * sizeof(int32_t), G * sizeof(int32_t), Sb,
+                                               cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));
             }
         } else if (!host_out) {
@@ -852,12 +856,12 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
                 const int64_t g1 = std::min<int64_t>(G, (int64_t)a.p1 * engine->Gp);
                 for (int t = 0; t < 4; ++t)
                     if (outs[t])
-                        CUDA_TRY(cudaMemcpy2DAsync(outs[t] + s0 * G + g0, G * sizeof(double),
+                        CUDA_TRY(cudaMemcpy2DAsync(outs[t] + s0 * out_row_stride + g0, out_row_stride * sizeof(double),
                                                    engine->out_f64[t].p + g0, G * sizeof(double),
                                                    (g1 - g0) * sizeof(double), Sb, cudaMemcpyDeviceToHost,
                                                    engine->copy_stream));
                 if (k)
-                    CUDA_TRY(cudaMemcpy2DAsync(k + s0 * G + g0, G * sizeof(int32_t), engine->out_k.p + g0,
+                    CUDA_TRY(cudaMemcpy2DAsync(k + s0 * out_row_stride + g0, out_row_stride * sizeof(int32_t), engine->out_k.p + g0,
                                                G * sizeof(int32_t), (g1 - g0) * sizeof(int32_t), Sb,
                                                cudaMemcpyDeviceToHost, engine->copy_stream));
             }
@@ -875,6 +879,24 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
         return engine->check_device_error("spade_run");
     }
     return SPADE_OK;
+}
+
+int spade_run(spade_engine *engine, const int32_t *members, int members_location,
+              const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
+              int32_t *k, int out_location, void *stream)
+{
+    return run_impl(engine, members, members_location, offsets, S, up, down, fc, cpm, k, out_location,
+                    engine ? engine->G : 0, stream);
+}
+
+int spade_run_strided(spade_engine *engine, const int32_t *members, int members_location,
+                      const int64_t *offsets, int64_t S, double *up, double *down, double *fc,
+                      double *cpm, int32_t *k, int out_location, int64_t out_row_stride, void *stream)
+{
+    if (!engine) return SPADE_ERR_ARG;
+    if (out_row_stride < engine->G) { set_error("out_row_stride must be >= G"); return SPADE_ERR_ARG; }
+    return run_impl(engine, members, members_location, offsets, S, up, down, fc, cpm, k, out_location,
+                    out_row_stride, stream);
 }
 
 int spade_timing(spade_engine *engine, double *test_ms, double *table_ms, int64_t *launches, int reset)
@@ -943,6 +965,61 @@ int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_
     return SPADE_OK;
 }
 
+#define IPC_TRY(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e);               \
+            return SPADE_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+
+int spade_device_alloc(int device, void **dptr, int64_t bytes)
+{
+    if (!dptr || bytes < 0) return SPADE_ERR_ARG;
+    IPC_TRY(cudaSetDevice(device));
+    IPC_TRY(cudaMalloc(dptr, (size_t)std::max<int64_t>(bytes, 1)));
+    return SPADE_OK;
+}
+
+int spade_device_free(int device, void *dptr)
+{
+    if (!dptr) return SPADE_OK;
+    IPC_TRY(cudaSetDevice(device));
+    IPC_TRY(cudaFree(dptr));
+    return SPADE_OK;
+}
+
+int spade_ipc_export(int device, void *dptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!dptr || !handle) return SPADE_ERR_ARG;
+    IPC_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    IPC_TRY(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, 64);
+    return SPADE_OK;
+}
+
+int spade_ipc_open(int device, const unsigned char handle[64], void **dptr)
+{
+    if (!dptr || !handle) return SPADE_ERR_ARG;
+    IPC_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    IPC_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SPADE_OK;
+}
+
+int spade_ipc_close(int device, void *dptr)
+{
+    if (!dptr) return SPADE_OK;
+    IPC_TRY(cudaSetDevice(device));
+    IPC_TRY(cudaIpcCloseMemHandle(dptr));
+    return SPADE_OK;
+}
+#undef IPC_TRY
+
 int spade_host_alloc(void **ptr, int64_t bytes)
 {
     if (!ptr || bytes < 0) return SPADE_ERR_ARG;
@@ -958,6 +1035,23 @@ int spade_host_free(void *ptr)
 {
     if (!ptr) return SPADE_OK;
     return cudaFreeHost(ptr) == cudaSuccess ? SPADE_OK : SPADE_ERR_CUDA;
+}
+
+int spade_host_register(void *ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return SPADE_ERR_ARG;
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e);
+        return SPADE_ERR_CUDA;
+    }
+    return SPADE_OK;
+}
+
+int spade_host_unregister(void *ptr)
+{
+    if (!ptr) return SPADE_OK;
+    return cudaHostUnregister(ptr) == cudaSuccess ? SPADE_OK : SPADE_ERR_CUDA;
 }
 
 }  // extern "C"

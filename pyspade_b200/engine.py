@@ -209,12 +209,15 @@ class Engine:
             raise ValueError("duplicate cell index inside a cell set")
 
     def run(self, sets=None, members=None, offsets=None, want_k=False, out=None, validate=True,
-            tables=TABLES):
+            tables=TABLES, row_stride=None):
         """Test every gene against each cell set.
 
         ``sets``: list of index arrays, or pass packed ``members`` + ``offsets``.
         Returns a dict of float64 arrays ``[S, G]`` (``up, down, fc, cpm``; plus int32 ``k``
-        when ``want_k``).  ``out`` may hold preallocated arrays (e.g. pinned) to fill."""
+        when ``want_k``).  ``out`` may hold preallocated arrays (e.g. pinned) to fill.  With
+        ``row_stride`` (elements) the arrays in ``out`` are strided views ``[S, G]`` of a larger
+        host table (row i of this call = row i of the view), e.g. a table shared by the ranks of
+        a node (:class:`pyspade_b200.shard.SharedHostTables`)."""
         if sets is not None:
             members, offsets = self.pack_sets(sets)
         members = np.asarray(members)
@@ -227,24 +230,36 @@ class Engine:
         for name in tables:
             if out is not None and name in out:
                 arr = out[name]
-                assert arr.dtype == np.float64 and arr.shape == (S, self.G) and arr.flags.c_contiguous
+                assert arr.dtype == np.float64 and arr.shape == (S, self.G)
+                if row_stride is None:
+                    assert arr.flags.c_contiguous
+                else:
+                    assert S <= 1 or arr.strides == (8 * row_stride, 8)
             else:
                 arr = np.empty((S, self.G), dtype=np.float64)
             res[name] = arr
         if want_k:
             res["k"] = (out["k"] if out is not None and "k" in out
                         else np.empty((S, self.G), dtype=np.int32))
-        self._check(self._lib.spade_run(
-            self._h, _ptr(members), _lib.SPADE_HOST, _ptr(offsets), S,
-            _ptr(res.get("up")), _ptr(res.get("down")), _ptr(res.get("fc")), _ptr(res.get("cpm")),
-            _ptr(res.get("k")), _lib.SPADE_HOST, None))
+        args = [self._h, _ptr(members), _lib.SPADE_HOST, _ptr(offsets), S,
+                _ptr(res.get("up")), _ptr(res.get("down")), _ptr(res.get("fc")), _ptr(res.get("cpm")),
+                _ptr(res.get("k")), _lib.SPADE_HOST]
+        if row_stride is None:
+            self._check(self._lib.spade_run(*args, None))
+        else:
+            if want_k and S > 1:
+                assert res["k"].strides == (4 * row_stride, 4)
+            self._check(self._lib.spade_run_strided(*args, int(row_stride), None))
         return res
 
-    def run_device(self, members, offsets_host, out, k=None, stream=None):
+    def run_device(self, members, offsets_host, out, k=None, stream=None, row_stride=None):
         """Device-resident form: ``members`` int32 torch tensor on this GPU,
-        ``offsets_host`` int64 numpy, ``out`` dict of float64 torch tensors ``[S, G]``.
-        Ordered on ``stream`` (a ``torch.cuda.Stream``; default: torch's current
-        stream); returns without synchronising."""
+        ``offsets_host`` int64 numpy, ``out`` dict of float64 torch tensors ``[S, G]`` - or raw
+        device addresses (``int``), e.g. into a table that lives on another GPU and was opened
+        with :class:`pyspade_b200.shard.PeerTables`.  ``row_stride`` (elements between the rows
+        of consecutive sets, default G) lets several ranks interleave their rows in one table.
+        Ordered on ``stream`` (a ``torch.cuda.Stream``; default: torch's current stream);
+        returns without synchronising."""
         import torch
 
         offsets = np.ascontiguousarray(offsets_host, dtype=np.int64)
@@ -252,21 +267,25 @@ class Engine:
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
 
-        def dp(t):
+        def dp(t, dtype=None):
             if t is None:
                 return None
+            if isinstance(t, int):
+                return ctypes.c_void_p(t)
             assert t.is_cuda and t.is_contiguous()
+            if dtype is not None:
+                assert t.dtype == dtype and tuple(t.shape) == (S, self.G)
             return ctypes.c_void_p(t.data_ptr())
 
-        for name in TABLES:
-            t = out.get(name)
-            if t is not None:
-                assert t.dtype == torch.float64 and tuple(t.shape) == (S, self.G)
         assert members.dtype == torch.int32
-        self._check(self._lib.spade_run(
-            self._h, dp(members), _lib.SPADE_DEVICE, _ptr(offsets), S,
-            dp(out.get("up")), dp(out.get("down")), dp(out.get("fc")), dp(out.get("cpm")),
-            dp(k), _lib.SPADE_DEVICE, ctypes.c_void_p(stream.cuda_stream)))
+        args = [self._h, dp(members), _lib.SPADE_DEVICE, _ptr(offsets), S,
+                dp(out.get("up"), torch.float64), dp(out.get("down"), torch.float64),
+                dp(out.get("fc"), torch.float64), dp(out.get("cpm"), torch.float64), dp(k, torch.int32)]
+        if row_stride is None:
+            self._check(self._lib.spade_run(*args, _lib.SPADE_DEVICE, ctypes.c_void_p(stream.cuda_stream)))
+        else:
+            self._check(self._lib.spade_run_strided(*args, _lib.SPADE_DEVICE, int(row_stride),
+                                                    ctypes.c_void_p(stream.cuda_stream)))
 
     def timing(self, reset=False):
         a, f, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()

@@ -7,6 +7,7 @@ tensors, gloo for the CPU tests).  Sets are always generated / enumerated on eve
 the same global order before they are split, so the tables do not depend on the number of
 ranks: sums are integer, tails are a pure function of (k, M, n, N).
 """
+import ctypes
 import os
 
 import numpy as np
@@ -74,33 +75,220 @@ def gather_rows(local, assignment, rank, world_size, n_cols, group=None):
     return out
 
 
-def run_sharded(engine, sets, tables=("up", "down", "fc", "cpm"), balance=False, want_k=False):
+class PeerTables:
+    """Result tables that live in rank 0's HBM and are mapped into every rank of the node.
+
+    Rank 0 allocates ``rows x cols`` elements per table (``spade_device_alloc``), exports
+    CUDA IPC handles, the other ranks open them (``spade_ipc_open``, peer access over
+    NVLink / NVSwitch).  A rank passes ``address(name, first_row)`` to
+    ``Engine.run_device(..., row_stride=...)``: the test kernel then stores its results
+    directly into rank 0's memory while it computes - the gather is fused into the kernel and
+    needs no collective, only a barrier before rank 0 reads.  ``torch.distributed`` is used for
+    the handle exchange and the barrier."""
+
+    ITEM = {"up": 8, "down": 8, "fc": 8, "cpm": 8, "k": 4}
+
+    def __init__(self, names, rows, cols, rank, world_size, device):
+        import torch.distributed as dist
+
+        from . import _lib
+        self._lib = _lib.load()
+        self.names, self.rows, self.cols = list(names), int(rows), int(cols)
+        self.rank, self.device = rank, device
+        self.ptr = {}
+        handles = [None]
+        if rank == 0:
+            hs = {}
+            for name in self.names:
+                p = ctypes.c_void_p()
+                self._ok(self._lib.spade_device_alloc(device, ctypes.byref(p),
+                                                      self.rows * self.cols * self.ITEM[name]))
+                buf = ctypes.create_string_buffer(64)
+                self._ok(self._lib.spade_ipc_export(device, p, buf))
+                self.ptr[name] = p.value
+                hs[name] = bytes(buf.raw)
+            handles = [hs]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            for name in self.names:
+                p = ctypes.c_void_p()
+                self._ok(self._lib.spade_ipc_open(device, handles[0][name], ctypes.byref(p)))
+                self.ptr[name] = p.value
+
+    def _ok(self, rc):
+        if rc != 0:
+            raise RuntimeError("peer tables: " + self._lib.spade_last_error(None).decode())
+
+    def address(self, name, first_row=0, first_col=0):
+        return self.ptr[name] + (first_row * self.cols + first_col) * self.ITEM[name]
+
+    def tensor(self, name):
+        """Rank 0: the table as a torch tensor (no copy)."""
+        import torch
+
+        assert self.rank == 0
+        dtype, typestr = (torch.int32, "<i4") if name == "k" else (torch.float64, "<f8")
+
+        class _View:
+            pass
+
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.rows, self.cols), "typestr": typestr,
+                                      "data": (self.ptr[name], False), "version": 2}
+        t = torch.as_tensor(v, device=torch.device("cuda", self.device))
+        assert t.dtype == dtype
+        return t
+
+    def close(self):
+        for name, p in self.ptr.items():
+            if self.rank == 0:
+                self._lib.spade_device_free(self.device, ctypes.c_void_p(p))
+            else:
+                self._lib.spade_ipc_close(self.device, ctypes.c_void_p(p))
+        self.ptr = {}
+
+
+class SharedHostTables:
+    """Result tables in host memory shared by the ranks of one node (POSIX shared memory,
+    ``/dev/shm``), page-locked in every rank (``spade_host_register``).  Each rank hands
+    strided views of its own rows to ``Engine.run(..., row_stride=...)``: every GPU then
+    delivers its rows over its own PCIe link, in parallel, and rank 0 reads the complete
+    tables from the same mapping after a barrier.  No GPU-to-GPU traffic at all - the right
+    path when the tables are wanted on the host (file writers, the e2e benchmark)."""
+
+    DTYPE = {"up": np.float64, "down": np.float64, "fc": np.float64, "cpm": np.float64, "k": np.int32}
+
+    def __init__(self, names, rows, cols, rank, world_size, pin=True, directory="/dev/shm"):
+        import torch.distributed as dist
+
+        from . import _lib
+        self._lib = _lib.load()
+        self.names, self.rows, self.cols, self.rank = list(names), int(rows), int(cols), rank
+        need = sum(self.rows * self.cols * np.dtype(self.DTYPE[n]).itemsize for n in self.names)
+        tag = [None]
+        if rank == 0:
+            st = os.statvfs(directory)
+            if st.f_bavail * st.f_frsize < need + (64 << 20):
+                tag = [""]                                   # not enough shared memory
+            else:
+                tag = [f"spade_b200_{os.getpid()}_{np.random.default_rng().integers(1 << 30)}"]
+        dist.broadcast_object_list(tag, src=0)
+        if not tag[0]:
+            raise MemoryError(f"{directory} cannot hold {need} bytes of result tables")
+        self.paths = {n: os.path.join(directory, f"{tag[0]}_{n}") for n in self.names}
+        self.arrays, self._pinned = {}, []
+        if rank == 0:
+            for n in self.names:
+                self.arrays[n] = np.memmap(self.paths[n], dtype=self.DTYPE[n], mode="w+",
+                                           shape=(self.rows, self.cols))
+        dist.barrier()
+        if rank != 0:
+            for n in self.names:
+                self.arrays[n] = np.memmap(self.paths[n], dtype=self.DTYPE[n], mode="r+",
+                                           shape=(self.rows, self.cols))
+        if pin:
+            for n in self.names:
+                a = self.arrays[n]
+                if self._lib.spade_host_register(ctypes.c_void_p(a.ctypes.data), a.nbytes) == 0:
+                    self._pinned.append(a.ctypes.data)
+        dist.barrier()
+        if rank == 0:                                        # mappings stay valid after unlink
+            for pth in self.paths.values():
+                os.unlink(pth)
+
+    def rows_view(self, name, first_row, row_step=1, count=None):
+        v = self.arrays[name][first_row::row_step]
+        return v if count is None else v[:count]
+
+    def close(self):
+        for p in self._pinned:
+            self._lib.spade_host_unregister(ctypes.c_void_p(p))
+        self._pinned = []
+        self.arrays = {}
+
+
+_SHARED = {}
+
+
+def _shared_tables(names, rows, cols, rank, world_size):
+    """One set of shared host tables per (names, cols), grown when more rows are needed."""
+    key = (tuple(names), cols)
+    cur = _SHARED.get(key)
+    if cur is not None and cur.rows >= rows:
+        return cur
+    if cur is not None:
+        cur.close()
+    _SHARED[key] = SharedHostTables(names, rows, cols, rank, world_size)
+    return _SHARED[key]
+
+
+def run_sharded(engine, sets, tables=("up", "down", "fc", "cpm"), balance=False, want_k=False,
+                gather="host"):
     """Run ``sets`` over all ranks of the torchrun job (or locally when there is one rank).
 
     Returns on rank 0 a dict of numpy arrays ``[S, G]`` in the order of ``sets``; ``None``
-    elsewhere.  With one rank this is ``engine.run``: host tables through the pipelined
-    device->host path.  With several ranks each rank keeps its tables on its GPU, one NCCL
-    gather brings them to rank 0, rank 0 copies them to the host."""
+    elsewhere.  With one rank this is ``engine.run``.  With several ranks:
+
+    * ``gather="host"`` (default): every rank writes its rows into host tables shared by the
+      node (:class:`SharedHostTables`), each GPU over its own PCIe link; falls back to
+      ``"nccl"`` when ``/dev/shm`` is too small;
+    * ``gather="nccl"``: every rank keeps its tables on its GPU, one NCCL gather per table
+      brings them to rank 0 over NVLink, rank 0 copies them to the host."""
     rank, local_rank, P = world()
     if P == 1:
         return engine.run(sets, tables=tables, want_k=want_k)
     import torch
     import torch.distributed as dist
 
+    gather = os.environ.get("SPADE_GATHER", gather)
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assignment = plan([len(s) for s in sets], P, balance=balance)
     mine = [sets[i] for i in assignment[rank]]
-    dev = torch.device("cuda", engine.device)
     members, offsets = engine.pack_sets(mine)
     engine._validate_members(members, offsets)
-    out = {k: torch.empty((len(mine), engine.G), dtype=torch.float64, device=dev) for k in tables}
-    kd = torch.empty((len(mine), engine.G), dtype=torch.int32, device=dev) if want_k else None
+    names = list(tables) + (["k"] if want_k else [])
+    S, G = len(sets), engine.G
+
+    if gather == "host":
+        try:
+            shared = _shared_tables(names, S, G, rank, P)
+        except MemoryError:
+            gather = "nccl"
+    if gather == "host":
+        if balance:        # contiguous block per rank, rows put back in set order by rank 0
+            first = int(sum(len(a) for a in assignment[:rank]))
+            out = {n: shared.rows_view(n, first, 1, len(mine)) for n in names}
+            stride = G
+        else:              # round-robin: set i of rank r is row i*P + r
+            out = {n: shared.rows_view(n, rank, P, len(mine)) for n in names}
+            stride = P * G
+        if len(mine):
+            engine.run(members=members, offsets=offsets, out=out, validate=False, tables=tables,
+                       want_k=want_k, row_stride=stride)
+        dist.barrier()
+        res = None
+        if rank == 0:
+            if balance:
+                order = np.concatenate(assignment)
+                res = {}
+                for n in names:
+                    full = np.empty((S, G), dtype=shared.DTYPE[n])
+                    full[order] = shared.arrays[n][:S]
+                    res[n] = full
+            else:
+                res = {n: np.array(shared.arrays[n][:S]) for n in names}
+        dist.barrier()                                   # tables may be overwritten after this
+        return res
+
+    dev = torch.device("cuda", engine.device)
+    out = {k: torch.empty((len(mine), G), dtype=torch.float64, device=dev) for k in tables}
+    kd = torch.empty((len(mine), G), dtype=torch.int32, device=dev) if want_k else None
     dmem = torch.from_numpy(members.astype(np.int32)).to(dev)
     engine.run_device(dmem, offsets, out, k=kd)
     if want_k:
         out["k"] = kd
-    full = gather_rows(out, assignment, rank, P, engine.G)
+    full = gather_rows(out, assignment, rank, P, G)
     torch.cuda.synchronize(dev)
     if rank != 0:
         return None

@@ -206,3 +206,43 @@ def test_gather_rows_world_size_2_gloo(balance):
     S = len(sizes)
     assert np.array_equal(full["up"], np.arange(S)[:, None] + np.arange(n_cols)[None, :] / 1000.0)
     assert np.array_equal(full["k"], np.arange(S)[:, None] * 7 + np.arange(n_cols)[None, :])
+
+
+def _shm_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        S, G = 7, 11                                              # 4 rows for rank 0, 3 for rank 1
+        t = shard.SharedHostTables(("up", "k"), S, G, rank, world, pin=False)
+        mine = np.arange(rank, S, world)
+        t.rows_view("up", rank, world, len(mine))[:] = mine[:, None] + np.arange(G)[None, :] / 100.0
+        t.rows_view("k", rank, world, len(mine))[:] = mine[:, None] * 3 + np.arange(G)[None, :]
+        assert t.rows_view("up", rank, world, len(mine)).strides == (8 * world * G, 8)
+        dist.barrier()
+        if rank == 0:
+            q.put({"up": np.array(t.arrays["up"]), "k": np.array(t.arrays["k"])})
+        else:
+            q.put(None)
+        dist.barrier()
+        t.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_host_tables_world_size_2_gloo():
+    """Rows written by two processes into the node-shared host tables, read back by rank 0."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = next(g for g in got if g is not None)
+    assert np.array_equal(full["up"], np.arange(7)[:, None] + np.arange(11)[None, :] / 100.0)
+    assert np.array_equal(full["k"], np.arange(7)[:, None] * 3 + np.arange(11)[None, :])

@@ -21,8 +21,8 @@ def _ngpu():
         return 0
 
 
-def _torchrun(nproc, args, port):
-    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+def _torchrun(nproc, args, port, gather="host"):
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), SPADE_GATHER=gather)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "pyspade_b200"] + args
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
@@ -30,15 +30,15 @@ def _torchrun(nproc, args, port):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("bg", ["complement", "NonTarget"])
-def test_two_rank_cli_matches_reference_files(tmp_path, cli_case, bg):
+@pytest.mark.parametrize("bg,gather", [("complement", "host"), ("NonTarget", "host"), ("complement", "nccl")])
+def test_two_rank_cli_matches_reference_files(tmp_path, cli_case, bg, gather):
     tpk, spk, dtx = _write_inputs(str(tmp_path), cli_case)
     od = str(tmp_path / "obs")
     os.makedirs(od)
-    _torchrun(2, ["DEobs", "-t", tpk, "-s", spk, "-d", dtx, "-o", od, "-b", bg], 29611)
+    _torchrun(2, ["DEobs", "-t", tpk, "-s", spk, "-d", dtx, "-o", od, "-b", bg], 29611, gather)
     _compare(_read_outputs(od), cli_case, f"DEobs/{bg}/")
     od = str(tmp_path / "rand") + "/"
     os.makedirs(od)
     _torchrun(2, ["DErand", "-t", tpk, "-s", spk, "-d", dtx, "-o", od, "-b", bg, "-m", "20", "-i", "56",
-                  "-a", "equal"], 29612)
+                  "-a", "equal"], 29612, gather)
     _compare(_read_outputs(od), cli_case, f"DErand/{bg}/equal/")
