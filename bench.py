@@ -266,14 +266,17 @@ def main():
     peer = None
     gather_mode = "none"
     if world > 1:
-        # Preferred: rank 0's [S*world, G] tables mapped into every rank (CUDA IPC); each rank's
-        # test kernel stores its rows (set i of rank r = row i*world + r) straight into rank 0's
-        # HBM over NVLink.  Fallback: one NCCL gather per table.
+        # Preferred: two [world*S, G] buffers of raw accumulator words in rank 0's HBM mapped into
+        # every rank (CUDA IPC).  A peer's test kernel stores its 8-byte words straight into rank
+        # 0's memory over NVLink while it computes (3x fewer bytes than the three float64
+        # tables); rank 0 writes its own rows directly and finishes the peers' rows with
+        # k_expand (set i of rank r = row i*world + r of the final tables).
+        # Fallback: one NCCL gather per table.
         from pyspade_b200 import shard
         ok = torch.ones(1, device=dev)
         if args.gather == "p2p":
             try:
-                peer = shard.PeerTables(TABLES, S * world, G, rank, world, local_rank)
+                peer = [shard.PeerTables(["raw"], S * world, G, rank, world, local_rank) for _ in range(2)]
             except Exception as exc:                                   # noqa: BLE001
                 print(f"[rank {rank}] peer tables unavailable: {exc}", file=sys.stderr)
                 ok.zero_()
@@ -281,16 +284,36 @@ def main():
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if float(ok) > 0:
-            gather_mode = "p2p stores into rank 0 from inside the test kernel (CUDA IPC over NVLink)"
+            gather_mode = ("raw accumulator words stored into rank 0 from inside the test kernel "
+                           "(CUDA IPC over NVLink), finished on rank 0 by k_expand")
         else:
             if peer is not None:
-                peer.close()
+                for pt in peer:
+                    pt.close()
                 peer = None
             gather_mode = "nccl gather of up/down/cpm tables to rank 0"
             if rank == 0:
                 gathered = {k: [torch.empty((S, G), dtype=torch.float64, device=dev) for _ in range(world)]
                             for k in TABLES}
     step_flag = torch.zeros(1, device=dev)
+    final = None
+    if peer is not None and rank == 0:
+        final = {k: torch.empty((S * world, G), dtype=torch.float64, device=dev) for k in TABLES}
+    peer_sizes = np.full(S, N, dtype=np.int64)
+    step_no = [0]
+
+    def step_peer(dmem, offsets):
+        buf = peer[step_no[0] & 1]          # peers fill one buffer while rank 0 expands the other
+        step_no[0] += 1
+        if rank == 0:
+            eng.run_device(dmem, offsets, {k: final[k].data_ptr() for k in TABLES}, row_stride=world * G)
+            dist.all_reduce(step_flag)      # passes once every peer's words have landed
+            for r in range(1, world):
+                eng.expand(buf.address("raw", first_row=r * S), peer_sizes,
+                           {k: final[k].data_ptr() + 8 * r * G for k in TABLES}, row_stride=world * G)
+        else:
+            eng.run_raw(dmem, offsets, buf.address("raw", first_row=rank * S))
+            dist.all_reduce(step_flag)
 
     def gather_tables():
         if world == 1:
@@ -301,9 +324,7 @@ def main():
     def step_device(i):
         _, _, offsets, dmem = batches[i % n_batches]
         if peer is not None:
-            eng.run_device(dmem, offsets, {k: peer.address(k, first_row=rank) for k in TABLES},
-                           row_stride=world * G)
-            dist.all_reduce(step_flag)          # rank 0 passes this point once every rank's rows landed
+            step_peer(dmem, offsets)
         else:
             eng.run_device(dmem, offsets, out_dev)
             gather_tables()
@@ -342,12 +363,10 @@ def main():
             return
         dmem = torch.from_numpy(members).to(dev, non_blocking=True)          # H2D of the index lists
         if peer is not None:
-            eng.run_device(dmem, offsets, {k: peer.address(k, first_row=rank) for k in TABLES},
-                           row_stride=world * G)
-            dist.all_reduce(step_flag)
+            step_peer(dmem, offsets)
             if rank == 0:
                 for k in TABLES:
-                    host_out_t[k].copy_(peer.tensor(k), non_blocking=True)
+                    host_out_t[k].copy_(final[k], non_blocking=True)
         else:
             eng.run_device(dmem, offsets, out_dev)
             gather_tables()
@@ -476,7 +495,7 @@ def main():
             eng.run_device(torch.from_numpy(m2).to(dev), o2, chk)
             torch.cuda.synchronize()
             same = all(bool(torch.equal(chk[k].view(torch.int64),
-                                        peer.tensor(k)[other::world][:4].view(torch.int64))) for k in TABLES)
+                                        final[k][other::world][:4].view(torch.int64))) for k in TABLES)
             line["multi_gpu_check"] = {"rows_of_rank": other, "sets": 4, "bit_identical": same}
         dist.barrier()
     if rank == 0:
@@ -484,7 +503,8 @@ def main():
     if world > 1:
         dist.barrier()
         if peer is not None:
-            peer.close()
+            for pt in peer:
+                pt.close()
         dist.destroy_process_group()
 
 

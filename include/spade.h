@@ -162,6 +162,22 @@ int spade_run_strided(spade_engine *engine, const int32_t *members, int members_
                       void *stream);
 
 /*
+ * Raw form of the batched test, for a result that has to cross a link: instead of the
+ * finished tables, store the 64-bit accumulator word of every test (member count << 48 | member
+ * sum in the gene's fixed point; 8 bytes per test instead of 24-36) into raw[S][out_row_stride]
+ * (device memory, possibly a peer GPU's).  spade_expand, on an engine staged from the same
+ * matrix with the same background, turns rows of such words into the tables - bit-identical to
+ * what spade_run would have written.  set_sizes: host int64[rows], N of every row's set.
+ * Sets above SPADE_OPT_MEMBER_BLOCK cells are refused by the raw form.
+ */
+int spade_run_raw(spade_engine *engine, const int32_t *members, int members_location,
+                  const int64_t *offsets, int64_t S, uint64_t *raw, int64_t out_row_stride,
+                  void *stream);
+int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_t raw_row_stride,
+                 const int64_t *set_sizes, double *up, double *down, double *fc, double *cpm,
+                 int32_t *k, int64_t out_row_stride, void *stream);
+
+/*
  * Plain device memory that can be shared between the processes of one node (one process per
  * GPU): the owner allocates and exports a 64-byte handle, peers open it and get a device
  * pointer valid in their own process (peer access over NVLink / NVSwitch).  Thin wrappers of

@@ -142,9 +142,9 @@ def DE_random_cells(sub_df_file,
         return
 
     spio.write_cell_ids(output_dir + '/' + str(num_cell) + '-rand_cell_ID.txt', draws)
-    spio.save_draw_table('%s/%s-up_log-pval' % (output_dir, num_cell), res["up"])
-    spio.save_draw_table('%s/%s-down_log-pval' % (output_dir, num_cell), res["down"])
-    spio.save_draw_table('%s/%s-cpm' % (output_dir, num_cell), res["cpm"])
+    spio.save_draw_tables([('%s/%s-up_log-pval' % (output_dir, num_cell), res["up"]),
+                           ('%s/%s-down_log-pval' % (output_dir, num_cell), res["down"]),
+                           ('%s/%s-cpm' % (output_dir, num_cell), res["cpm"])])
 
     logger.info('Start modeling randomization distribution.')
     cpm_mean = np.mean(res["cpm"], axis=0)

@@ -41,6 +41,11 @@ SIGNATURES = {
                                          ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                          ctypes.c_void_p]),
+    "spade_run_raw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "spade_expand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "spade_device_alloc": (ctypes.c_int, [ctypes.c_int, c_vpp, ctypes.c_int64]),
     "spade_device_free": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "spade_ipc_export": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p]),

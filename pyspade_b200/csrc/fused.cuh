@@ -113,6 +113,8 @@ struct RunArgs {
     int64_t nblk;
     unsigned long long *gsum;     // [S][G] global accumulators of split mode
     int *gcnt;
+    unsigned long long *raw;      // non-null: store the accumulator words instead of finished tests
+    int64_t raw_ld;
     int p0, p1;                   // gene partitions of this launch
     int Gp;
     int64_t C;
@@ -269,7 +271,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         __syncwarp();
     }
 
-    if (!kSplit) {
+    if (!kSplit && a.raw) {
+        // raw form: the accumulator words leave as they are (8 bytes per test instead of 24-36);
+        // whoever receives them finishes the tests with k_expand
+        for (int j = lane; j < ng; j += 32) a.raw[row * a.raw_ld + g0 + j] = acc[j];
+    } else if (!kSplit) {
         const double invN = 1.0 / (double)N;
         const double invRest = 1.0 / (double)((long long)a.C - N);
         for (int j = lane; j < ng; j += 32) {
@@ -303,6 +309,84 @@ k_finalize_split(const FinCtx f, const unsigned long long *__restrict__ gsum,
     const long long N = offsets[s0 + row + 1] - offsets[s0 + row];
     finalize_test(f, row, g, (long long)gsum[idx], gcnt[idx], N, 1.0 / (double)N,
                   1.0 / (double)((long long)f.M - N));
+}
+
+// After the segmented sort a duplicated cell index inside a set sits next to its twin.
+__global__ void k_check_duplicates(const int32_t *__restrict__ sorted, const int64_t *__restrict__ offsets,
+                                   int64_t S, int64_t total, int *__restrict__ err)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i + 1 < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (sorted[i] != sorted[i + 1]) continue;
+        // same set?  i + 1 must not be the first member of a set
+        int64_t lo = 0, hi = S;                      // first s with offsets[s] > i
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (offsets[mid] > i) hi = mid; else lo = mid + 1;
+        }
+        if (lo > S || offsets[lo] != i + 1) atomicExch(err, 4);
+    }
+}
+
+// Finish tests from raw accumulator words (k_de_fused raw form), e.g. words another GPU stored
+// into this GPU's memory.  sizes[row] = N of the row's cell set.  A thread owns one gene and
+// walks kExpandRows rows: the gene's metadata is read once, raw reads and table writes are
+// coalesced across the genes of a warp.
+constexpr int kExpandRows = 16;
+
+__global__ void __launch_bounds__(256)
+k_expand(const FinCtx f, const unsigned long long *__restrict__ raw, int64_t raw_ld,
+         const int64_t *__restrict__ sizes, int64_t rows)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= f.G) return;
+    const int64_t r0 = (int64_t)blockIdx.y * kExpandRows;
+    const int64_t r1 = min(rows, r0 + kExpandRows);
+    const GeneMeta mt = f.meta[g];
+    const double inv = pow2_double(-mt.shift);
+    TabMeta tm;
+    tm.off = 0; tm.lo = 0; tm.len = 0;
+    if (f.tmeta) tm = f.tmeta[g];
+    unsigned long long w[kExpandRows];
+#pragma unroll
+    for (int i = 0; i < kExpandRows; ++i)
+        w[i] = r0 + i < r1 ? __ldcs(raw + (r0 + i) * raw_ld + g) : 0ull;
+#pragma unroll
+    for (int i = 0; i < kExpandRows; ++i) {
+        const int64_t row = r0 + i;
+        if (row >= r1) break;
+        const long long v = (long long)w[i];
+        const long long sumfx = (v << 16) >> 16;
+        const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
+        const long long N = sizes[row];
+        const int kk = mt.negmode ? cnt : (int)(N - cnt);
+        const double mean_set = ((double)sumfx * inv) * (1.0 / (double)N);
+        const int64_t o = row * f.ld + g;
+        if (f.cpm) __stcs(f.cpm + o, mean_set);
+        if (f.fc) {
+            const double mean_bg = f.nc_mode ? mt.bgmean
+                                             : ((double)(mt.rowsum - sumfx) * inv) * (1.0 / (double)((long long)f.M - N));
+            __stcs(f.fc + o, (mean_set + 0.01) / (mean_bg + 0.01));
+        }
+        if (f.k) f.k[o] = kk;
+        if (f.up || f.down) {
+            double lc, ls;
+            if (kk == 0 || f.M == 0 || mt.n == 0 || N == 0) {
+                lc = ls = __longlong_as_double(0x7ff8000000000000ll);
+            } else {
+                const unsigned d = (unsigned)(kk - tm.lo);
+                if (d < (unsigned)tm.len) {
+                    const double2 t = f.tab[tm.off + d];
+                    lc = t.x;
+                    ls = t.y;
+                } else {
+                    hyper_tails(kk, f.M, mt.n, (int)N, f.lf, lc, ls);
+                }
+            }
+            if (f.up) __stcs(f.up + o, lc);
+            if (f.down) __stcs(f.down + o, ls);
+        }
+    }
 }
 
 }  // namespace spade

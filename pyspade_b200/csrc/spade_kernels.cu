@@ -112,6 +112,8 @@ struct spade_engine {
     cudaStream_t work[2] = {nullptr, nullptr}, copy_stream = nullptr;
     cudaEvent_t ev_ready = nullptr;
     std::vector<cudaEvent_t> sync_events;
+    int64_t tab_N = -1;                // set size the tail table on the device was built for
+    int64_t tab_epoch = -1, bg_epoch = 0;
     PinnedBuf<TabMeta> h_tmeta;
     PinnedBuf<int64_t> h_offsets;
 
@@ -171,6 +173,7 @@ struct spade_engine {
             CUDA_TRY(cudaMemset(err.p, 0, sizeof(int)));
             const char *m = h == 2   ? ": member cell index out of range"
                             : h == 3 ? ": matrix holds non-finite (or > 8e270) values"
+                            : h == 4 ? ": duplicate cell index inside a cell set"
                                      : ": cell index out of range in the matrix";
             set_error(std::string(what) + m);
             return SPADE_ERR_ARG;
@@ -181,6 +184,7 @@ struct spade_engine {
     // K1 + entry scatter; re-run whenever the background changes.
     int stage_genes(cudaStream_t st)
     {
+        ++bg_epoch;                    // cutoffs change: any tail table on the device is stale
         const size_t np = (size_t)P * (size_t)C;
         if (np > 0) {
             k_init_cursor<<<grid_for(np, 256), 256, 0, st>>>(pptr.p, (int64_t)np, C, dense_on.p, cursor.p);
@@ -365,6 +369,7 @@ struct spade_engine {
     int build_tail_table(int64_t N, cudaStream_t st, bool *built)
     {
         *built = false;
+        tab_N = -1;
         CUDA_TRY(h_tmeta.reserve((size_t)G));
         const double M = (double)C;
         unsigned long long total = 0;
@@ -404,6 +409,8 @@ struct spade_engine {
         if (rc != SPADE_OK) return rc;
         launches += 1;
         *built = true;
+        tab_N = N;
+        tab_epoch = bg_epoch;
         return SPADE_OK;
     }
 
@@ -656,7 +663,8 @@ int spade_cpm_values(spade_engine *engine, double *values)
 
 static int run_impl(spade_engine *engine, const int32_t *members, int members_location,
                     const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
-                    int32_t *k, int out_location, int64_t out_row_stride, void *stream)
+                    int32_t *k, int out_location, int64_t out_row_stride, void *stream,
+                    unsigned long long *raw = nullptr)
 {
     if (!engine) return SPADE_ERR_ARG;
     CUDA_TRY(cudaSetDevice(engine->device));
@@ -701,7 +709,9 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
         CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(engine->sort_temp.p, tb, d_members, engine->members_sorted.p,
                                                     total, S, engine->offsets.p, engine->offsets.p + 1, st));
         d_members = engine->members_sorted.p;
-        engine->launches += 1;
+        k_check_duplicates<<<grid_for(total, 256), 256, 0, st>>>(d_members, engine->offsets.p, S, total, engine->err.p);
+        CUDA_TRY(cudaGetLastError());
+        engine->launches += 2;
     }
 
     const bool host_out = out_location == SPADE_HOST;
@@ -725,6 +735,10 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             uniform &= (N == N0);
         }
         const bool split = maxN > engine->member_block;
+        if (split && raw) {
+            set_error("the raw form takes sets of at most SPADE_OPT_MEMBER_BLOCK cells");
+            return SPADE_ERR_ARG;
+        }
         if (split && (s1 - s0) * G > kMaxTestsSplitChunk) {
             s1 = s0 + std::max<int64_t>(1, kMaxTestsSplitChunk / G);
             uniform = true;
@@ -733,7 +747,7 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
         const int64_t Sb = s1 - s0;
 
         bool table = false;
-        if (uniform && N0 > 0 && (engine->tail_mode == 2 || (engine->tail_mode == 1 && Sb >= 32))) {
+        if (!raw && uniform && N0 > 0 && (engine->tail_mode == 2 || (engine->tail_mode == 1 && Sb >= 32))) {
             int rc = engine->build_tail_table(N0, st, &table);
             if (rc != SPADE_OK) return rc;
         }
@@ -751,6 +765,8 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
         a.Gp = engine->Gp;
         a.C = C;
         a.err = engine->err.p;
+        a.raw = raw ? raw + s0 * out_row_stride : nullptr;
+        a.raw_ld = out_row_stride;
         a.fin.G = G;
         a.fin.M = (int)C;
         a.fin.nc_mode = engine->n_nc > 0;
@@ -897,6 +913,66 @@ int spade_run_strided(spade_engine *engine, const int32_t *members, int members_
     if (out_row_stride < engine->G) { set_error("out_row_stride must be >= G"); return SPADE_ERR_ARG; }
     return run_impl(engine, members, members_location, offsets, S, up, down, fc, cpm, k, out_location,
                     out_row_stride, stream);
+}
+
+int spade_run_raw(spade_engine *engine, const int32_t *members, int members_location,
+                  const int64_t *offsets, int64_t S, uint64_t *raw, int64_t out_row_stride, void *stream)
+{
+    if (!engine) return SPADE_ERR_ARG;
+    if (!raw) { set_error("raw is NULL"); return SPADE_ERR_ARG; }
+    if (out_row_stride < engine->G) { set_error("out_row_stride must be >= G"); return SPADE_ERR_ARG; }
+    return run_impl(engine, members, members_location, offsets, S, nullptr, nullptr, nullptr, nullptr, nullptr,
+                    SPADE_DEVICE, out_row_stride, stream, (unsigned long long *)raw);
+}
+
+int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_t raw_row_stride,
+                 const int64_t *set_sizes, double *up, double *down, double *fc, double *cpm, int32_t *k,
+                 int64_t out_row_stride, void *stream)
+{
+    if (!engine) return SPADE_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(engine->device));
+    if (rows < 0 || !set_sizes || (rows > 0 && !raw)) { set_error("bad raw / rows / set_sizes"); return SPADE_ERR_ARG; }
+    if (raw_row_stride < engine->G || out_row_stride < engine->G) { set_error("row strides must be >= G"); return SPADE_ERR_ARG; }
+    if (rows == 0 || engine->G == 0) return SPADE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t G = engine->G;
+    bool uniform = true;
+    for (int64_t r = 0; r < rows; ++r) {
+        if (set_sizes[r] < 0 || set_sizes[r] > engine->C) { set_error("set size out of range"); return SPADE_ERR_ARG; }
+        uniform &= set_sizes[r] == set_sizes[0];
+    }
+    CUDA_TRY(engine->offsets.reserve(rows));
+    CUDA_TRY(engine->h_offsets.reserve(rows));
+    memcpy(engine->h_offsets.p, set_sizes, rows * sizeof(int64_t));
+    CUDA_TRY(engine->h_offsets.upload(engine->offsets.p, (size_t)rows, st));
+    bool table = false;
+    if (uniform && set_sizes[0] > 0 && (engine->tail_mode == 2 || (engine->tail_mode == 1 && rows >= 32))) {
+        if (engine->tab_N == set_sizes[0] && engine->tab_epoch == engine->bg_epoch) {
+            table = true;      // the table the last spade_run / spade_expand built for this N is still valid
+        } else {
+            int rc = engine->build_tail_table(set_sizes[0], st, &table);
+            if (rc != SPADE_OK) return rc;
+        }
+    }
+    FinCtx f;
+    f.G = G;
+    f.M = (int)engine->C;
+    f.nc_mode = engine->n_nc > 0;
+    f.meta = engine->meta.p;
+    f.tmeta = table ? engine->tmeta.p : nullptr;
+    f.tab = table ? engine->tab.p : nullptr;
+    f.lf = engine->lf.p;
+    f.up = up; f.down = down; f.fc = fc; f.cpm = cpm; f.k = k;
+    f.ld = out_row_stride;
+    int rc = engine->span_begin(st, 2);
+    if (rc != SPADE_OK) return rc;
+    const dim3 grid((unsigned)((G + 255) / 256), (unsigned)((rows + kExpandRows - 1) / kExpandRows));
+    k_expand<<<grid, 256, 0, st>>>(f, (const unsigned long long *)raw, raw_row_stride, engine->offsets.p, rows);
+    CUDA_TRY(cudaGetLastError());
+    rc = engine->span_end(st);
+    if (rc != SPADE_OK) return rc;
+    engine->launches += 1;
+    return SPADE_OK;
 }
 
 int spade_timing(spade_engine *engine, double *test_ms, double *table_ms, int64_t *launches, int reset)

@@ -67,6 +67,9 @@ class Engine:
         self.G, self.C, self.nnz, self.genes_per_part = G.value, C.value, nnz.value, f.value
         self.n_nc = 0
         self.background_key = None
+        # out-of-range and duplicated member cells are caught on the device (range check in the
+        # test kernel, adjacent-equal check after the member sort) unless the sort is disabled
+        self.device_validation = True
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -123,8 +126,12 @@ class Engine:
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc):
         if rc != _lib.SPADE_OK:
-            raise SpadeError(f"libspade_b200 error {rc}: "
-                             f"{self._lib.spade_last_error(self._h).decode()}")
+            msg = self._lib.spade_last_error(self._h).decode()
+            if "duplicate cell index inside a cell set" in msg:
+                raise ValueError(msg)                  # what the host-side validation raises
+            if "member cell index out of range" in msg:
+                raise IndexError(msg)
+            raise SpadeError(f"libspade_b200 error {rc}: {msg}")
 
     def close(self):
         if self._h is not None:
@@ -152,6 +159,8 @@ class Engine:
                "genes_per_part": _lib.SPADE_OPT_GENES_PER_PART,
                "sort_members": _lib.SPADE_OPT_SORT_MEMBERS}[name]
         self._check(self._lib.spade_set_option(self._h, opt, int(value)))
+        if name == "sort_members":
+            self.device_validation = bool(value)
         if name == "genes_per_part":
             f = ctypes.c_int32()
             self._check(self._lib.spade_dims(self._h, None, None, None, ctypes.byref(f)))
@@ -223,8 +232,10 @@ class Engine:
         members = np.asarray(members)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         S = offsets.shape[0] - 1
-        if validate:
+        if validate and not self.device_validation:
             self._validate_members(members.astype(np.int64, copy=False), offsets)
+        elif validate and members.shape[0] and (members.min() < -(1 << 31) or members.max() >= (1 << 31)):
+            raise IndexError("cell index out of range in a cell set")
         members = np.ascontiguousarray(members, dtype=np.int32)
         res = {}
         for name in tables:
@@ -286,6 +297,40 @@ class Engine:
         else:
             self._check(self._lib.spade_run_strided(*args, _lib.SPADE_DEVICE, int(row_stride),
                                                     ctypes.c_void_p(stream.cuda_stream)))
+
+    def run_raw(self, members, offsets_host, raw, row_stride=None, stream=None):
+        """Raw form (``spade_run_raw``): accumulator words, 8 bytes per test, into ``raw`` - a
+        uint64/int64 torch tensor ``[S, G]`` or a device address (e.g. on a peer GPU)."""
+        import torch
+
+        offsets = np.ascontiguousarray(offsets_host, dtype=np.int64)
+        S = offsets.shape[0] - 1
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        rp = ctypes.c_void_p(raw if isinstance(raw, int) else raw.data_ptr())
+        assert members.dtype == torch.int32
+        self._check(self._lib.spade_run_raw(self._h, ctypes.c_void_p(members.data_ptr()), _lib.SPADE_DEVICE,
+                                            _ptr(offsets), S, rp, int(row_stride or self.G),
+                                            ctypes.c_void_p(stream.cuda_stream)))
+
+    def expand(self, raw, set_sizes, out, k=None, raw_row_stride=None, row_stride=None, stream=None):
+        """``spade_expand``: finish the tests of ``len(set_sizes)`` rows of raw words into the
+        tables of ``out`` (torch tensors or device addresses)."""
+        import torch
+
+        sizes = np.ascontiguousarray(set_sizes, dtype=np.int64)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+
+        def dp(t):
+            if t is None:
+                return None
+            return ctypes.c_void_p(t if isinstance(t, int) else t.data_ptr())
+
+        self._check(self._lib.spade_expand(self._h, dp(raw), sizes.shape[0], int(raw_row_stride or self.G),
+                                           _ptr(sizes), dp(out.get("up")), dp(out.get("down")),
+                                           dp(out.get("fc")), dp(out.get("cpm")), dp(k),
+                                           int(row_stride or self.G), ctypes.c_void_p(stream.cuda_stream)))
 
     def timing(self, reset=False):
         a, f, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()

@@ -86,7 +86,7 @@ class PeerTables:
     needs no collective, only a barrier before rank 0 reads.  ``torch.distributed`` is used for
     the handle exchange and the barrier."""
 
-    ITEM = {"up": 8, "down": 8, "fc": 8, "cpm": 8, "k": 4}
+    ITEM = {"up": 8, "down": 8, "fc": 8, "cpm": 8, "k": 4, "raw": 8}
 
     def __init__(self, names, rows, cols, rank, world_size, device):
         import torch.distributed as dist
@@ -127,7 +127,7 @@ class PeerTables:
         import torch
 
         assert self.rank == 0
-        dtype, typestr = (torch.int32, "<i4") if name == "k" else (torch.float64, "<f8")
+        dtype, typestr = {"k": (torch.int32, "<i4"), "raw": (torch.int64, "<i8")}.get(name, (torch.float64, "<f8"))
 
         class _View:
             pass
@@ -246,7 +246,6 @@ def run_sharded(engine, sets, tables=("up", "down", "fc", "cpm"), balance=False,
     assignment = plan([len(s) for s in sets], P, balance=balance)
     mine = [sets[i] for i in assignment[rank]]
     members, offsets = engine.pack_sets(mine)
-    engine._validate_members(members, offsets)
     names = list(tables) + (["k"] if want_k else [])
     S, G = len(sets), engine.G
 
@@ -264,8 +263,8 @@ def run_sharded(engine, sets, tables=("up", "down", "fc", "cpm"), balance=False,
             out = {n: shared.rows_view(n, rank, P, len(mine)) for n in names}
             stride = P * G
         if len(mine):
-            engine.run(members=members, offsets=offsets, out=out, validate=False, tables=tables,
-                       want_k=want_k, row_stride=stride)
+            engine.run(members=members, offsets=offsets, out=out, tables=tables, want_k=want_k,
+                       row_stride=stride)
         dist.barrier()
         res = None
         if rank == 0:
@@ -281,6 +280,7 @@ def run_sharded(engine, sets, tables=("up", "down", "fc", "cpm"), balance=False,
         dist.barrier()                                   # tables may be overwritten after this
         return res
 
+    engine._validate_members(members, offsets)
     dev = torch.device("cuda", engine.device)
     out = {k: torch.empty((len(mine), G), dtype=torch.float64, device=dev) for k in tables}
     kd = torch.empty((len(mine), G), dtype=torch.int32, device=dev) if want_k else None

@@ -346,3 +346,35 @@ def test_layout_switches_do_not_change_results(monkeypatch):
     ora = de_port.de_tables(X, sets, nc, tail_fn=c_oracle.hypergeom_logcdf_logsf)
     assert np.array_equal(res[(1, 1)][1]["k"], ora["k"])
     assert_tables_close(res[(1, 1)][1], ora)
+
+
+@pytest.mark.parametrize("mode", ["complement", "nc"])
+def test_raw_form_and_expand_equal_direct_run(mode):
+    """spade_run_raw + spade_expand (what a peer GPU sends / what rank 0 finishes) give the
+    same bits as spade_run, uniform-N (tail table) and ragged (direct tails) batches."""
+    import torch
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 1500, 2600
+    counts = synth.counts_numpy(G, C, seed=23)
+    nc = np.arange(2, C, 19) if mode == "nc" else None
+    for sets in (synth.derand_draws(C, 90, 40), synth.deobs_sets(C, 7, lo=3, hi=700)):
+        members, offsets = synth.concat_sets(sets)
+        with Engine.from_counts(counts) as eng:
+            eng.set_background(nc)
+            want = eng.run(sets, want_k=True)
+            dm = torch.from_numpy(members).cuda()
+            raw = torch.zeros((len(sets), G + 5), dtype=torch.int64, device="cuda")       # padded rows
+            eng.run_raw(dm, offsets, raw, row_stride=G + 5)
+            out = {k: torch.full((len(sets), 2 * G), -7.0, dtype=torch.float64, device="cuda")
+                   for k in ("up", "down", "fc", "cpm")}
+            kd = torch.zeros((len(sets), 2 * G), dtype=torch.int32, device="cuda")
+            # tables interleaved with another "rank": this rank owns columns G..2G of each row
+            eng.expand(raw, [len(s) for s in sets], {k: v.data_ptr() + 8 * G for k, v in out.items()},
+                       k=kd.data_ptr() + 4 * G, raw_row_stride=G + 5, row_stride=2 * G)
+            torch.cuda.synchronize()
+        for name in out:
+            got = out[name].cpu().numpy()
+            assert np.array_equal(got[:, G:], want[name], equal_nan=True), name
+            assert (got[:, :G] == -7.0).all()
+        assert np.array_equal(kd.cpu().numpy()[:, G:], want["k"])

@@ -246,3 +246,32 @@ def test_shared_host_tables_world_size_2_gloo():
     full = next(g for g in got if g is not None)
     assert np.array_equal(full["up"], np.arange(7)[:, None] + np.arange(11)[None, :] / 100.0)
     assert np.array_equal(full["k"], np.arange(7)[:, None] * 3 + np.arange(11)[None, :])
+
+
+def test_mat_writers_load_like_scipy_written_files(tmp_path):
+    """The direct MAT-v5 writers against scipy.io.savemat: loadmat gives identical arrays,
+    identical sparse structure (stored nan / -inf, dropped +-0.0), also for empty tables."""
+    rng = np.random.default_rng(4)
+    vec = rng.normal(size=301)
+    vec[[0, 5]] = [np.nan, -np.inf]
+    vec[7] = 0.0
+    spio.save_vector(str(tmp_path / "a-b:c-up_log-pval"), vec)
+    sio.savemat(str(tmp_path / "ref_vec"), {"matrix": vec})
+    a, b = sio.loadmat(str(tmp_path / "a-b:c-up_log-pval"))["matrix"], sio.loadmat(str(tmp_path / "ref_vec"))["matrix"]
+    assert a.shape == b.shape == (1, 301) and a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+    for shape in ((56, 30), (3, 1), (1, 7), (40, 33)):
+        t = rng.normal(size=shape)
+        t[rng.random(shape) < 0.4] = 0.0
+        t[rng.random(shape) < 0.05] = -0.0
+        t[rng.random(shape) < 0.05] = np.nan
+        t[rng.random(shape) < 0.05] = -np.inf
+        for tab, tag in ((t, "x"), (np.zeros(shape), "z")):
+            spio.save_draw_table(str(tmp_path / f"mine_{tag}"), tab)
+            sio.savemat(str(tmp_path / f"ref_{tag}"), {"matrix": sp.csr_matrix(tab)})
+            m, r = sio.loadmat(str(tmp_path / f"mine_{tag}"))["matrix"], sio.loadmat(str(tmp_path / f"ref_{tag}"))["matrix"]
+            assert sp.issparse(m) and m.shape == r.shape and m.dtype == r.dtype and m.format == r.format
+            m, r = m.tocsc(), r.tocsc()
+            assert np.array_equal(m.indptr, r.indptr) and np.array_equal(m.indices, r.indices)
+            assert np.array_equal(m.data, r.data, equal_nan=True)
+    spio.save_draw_tables([(str(tmp_path / "p1"), t), (str(tmp_path / "p2"), -t)])
+    assert np.array_equal(np.asarray(sio.loadmat(str(tmp_path / "p2"))["matrix"].todense()), -t + 0.0, equal_nan=True)
