@@ -378,3 +378,25 @@ def test_raw_form_and_expand_equal_direct_run(mode):
             assert np.array_equal(got[:, G:], want[name], equal_nan=True), name
             assert (got[:, :G] == -7.0).all()
         assert np.array_equal(kd.cpu().numpy()[:, G:], want["k"])
+
+
+def test_fully_dense_matrix_long_segments():
+    """Every gene expressed in every cell: segments of ~1000 entries (the long-segment loop of
+    the test kernel), medians > 0 everywhere, ties, G not a multiple of the partition width."""
+    from pyspade_b200.engine import Engine
+    rng = np.random.default_rng(33)
+    G, C = 2091, 400
+    dense = rng.integers(1, 6, size=(G, C)).astype(np.float64)      # many ties
+    dense[5] = 3.0                                                  # constant gene: n = C
+    X = sp.csr_matrix(dense)
+    sets = [rng.choice(C, n, replace=False) for n in (1, 17, 200, 399)]
+    nc = rng.choice(C, 57, replace=False)
+    with Engine.from_cpm(X) as eng:
+        for bg in (None, nc):
+            eng.set_background(bg)
+            got = eng.run(sets, want_k=True)
+            med, n = eng.gene_cutoffs()
+            ora = de_port.de_tables(X, sets, bg, tail_fn=c_oracle.hypergeom_logcdf_logsf)
+            assert np.array_equal(med, ora["median"]) and np.array_equal(n, ora["n"])
+            assert np.array_equal(got["k"], ora["k"])
+            assert_tables_close(got, ora)
