@@ -400,3 +400,26 @@ def test_fully_dense_matrix_long_segments():
             assert np.array_equal(med, ora["median"]) and np.array_equal(n, ora["n"])
             assert np.array_equal(got["k"], ora["k"])
             assert_tables_close(got, ora)
+
+
+def test_strided_host_tables_interleave_like_two_ranks():
+    """Engine.run(row_stride=...): two 'ranks' (two calls) interleave their rows in one host
+    table, the layout shard.SharedHostTables gives every rank; plus the split path."""
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 1100, 1500
+    counts = synth.counts_numpy(G, C, seed=41)
+    sets = synth.derand_draws(C, 70, 9)
+    with Engine.from_counts(counts) as eng:
+        whole = eng.run(sets, want_k=True)
+        for block in (None, 32):
+            if block:
+                eng.set_option("member_block", block)           # sets of 70 cells take the split path
+            full = {n: np.full((9, G), -3.0) for n in ("up", "down", "fc", "cpm")}
+            full["k"] = np.full((9, G), -3, dtype=np.int32)
+            for r in range(2):
+                mine = sets[r::2]
+                out = {n: a[r::2] for n, a in full.items()}
+                eng.run(mine, out=out, want_k=True, row_stride=2 * G)
+            for name in whole:
+                assert np.array_equal(full[name], whole[name], equal_nan=True), (name, block)
