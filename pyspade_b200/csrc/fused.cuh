@@ -78,6 +78,9 @@ __device__ __forceinline__ void finalize_test(const FinCtx &f, int64_t row, int6
         double lc, ls;
         if (kk == 0 || f.M == 0 || mt.n == 0 || N == 0) {       // all([k, M, n, N]), utils.py:212-213
             lc = ls = __longlong_as_double(0x7ff8000000000000ll);
+        } else if (kk >= min(mt.n, (int)N)) {                   // upper support edge: no lookup needed
+            lc = 0.0;                                            // (what hyper_tails returns first)
+            ls = -INFINITY;
         } else {
             bool hit = false;
             if (f.tmeta) {
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     extern __shared__ unsigned long long smem_acc[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long *acc = smem_acc + (size_t)warp * a.Gp;
+    uint2 *mbuf = reinterpret_cast<uint2 *>(smem_acc + (size_t)kWarpsPerCta * a.Gp) + warp * 32;
 
     const int64_t units = kSplit ? a.nblk : a.S;
     const int64_t t = blockIdx.x * (int64_t)kWarpsPerCta + warp;
@@ -196,17 +200,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     constexpr int kBatchesPerGroup = 32 / kMemberBatch;
     auto load = [&](Batch &t, int ib) {
         const int grp = ib / kBatchesPerGroup, w = (ib % kBatchesPerGroup) * kMemberBatch;
-        if (w == 0) {                                  // entering a group: prefetch the next one
+        if (w == 0) {
+            // entering a group: park its 32 (begin, end) pairs in shared memory - one broadcast
+            // read per member costs a quarter of the two shuffles it replaces on the LSU data
+            // pipe - and prefetch the next group's pairs into the other register set
+            __syncwarp();
+            mbuf[lane] = (grp & 1) ? make_uint2(mb[1], me[1]) : make_uint2(mb[0], me[0]);
+            __syncwarp();
             if (grp & 1) fetch_meta(grp + 1, mb[0], me[0]);
             else fetch_meta(grp + 1, mb[1], me[1]);
         }
-        const uint32_t b = (grp & 1) ? mb[1] : mb[0], e = (grp & 1) ? me[1] : me[0];
 #pragma unroll
         for (int q = 0; q < kMemberBatch; ++q) {
-            const uint32_t bq = __shfl_sync(0xffffffffu, b, w + q);
-            t.ee[q] = __shfl_sync(0xffffffffu, e, w + q);
-            t.dv[q] = (dense && t.ee[q] != 0) ? stream_load(ent + bq + lane) : 0ull;
-            t.bb[q] = bq + head + lane;
+            const uint2 se = mbuf[w + q];
+            t.ee[q] = se.y;
+            t.dv[q] = (dense && se.y != 0) ? stream_load(ent + se.x + lane) : 0ull;
+            t.bb[q] = se.x + head + lane;
         }
 #pragma unroll
         for (int q = 0; q < kMemberBatch; ++q)

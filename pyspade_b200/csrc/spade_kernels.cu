@@ -335,9 +335,9 @@ struct spade_engine {
         if (rc != SPADE_OK) return rc;
 
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kWarpsPerCta * 4096 * 8));
+                                      kWarpsPerCta * (4096 + 32) * 8));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kWarpsPerCta * 4096 * 8));
+                                      kWarpsPerCta * (4096 + 32) * 8));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         return stage_genes(st);
@@ -421,7 +421,7 @@ struct spade_engine {
         if (tasks <= 0) return SPADE_OK;
         const int64_t blocks = (tasks + kWarpsPerCta - 1) / kWarpsPerCta;
         if (blocks > 0x7fffffffll) { set_error("batch too large for one launch"); return SPADE_ERR_ARG; }
-        const size_t smem = (size_t)kWarpsPerCta * Gp * sizeof(unsigned long long);
+        const size_t smem = (size_t)kWarpsPerCta * (Gp + 32) * sizeof(unsigned long long);   // accumulators + pair buffers
         int rc = span_begin(st, 0);
         if (rc != SPADE_OK) return rc;
         if (split) k_de_fused<true><<<(unsigned)blocks, kWarpsPerCta * 32, smem, st>>>(a);
