@@ -966,9 +966,20 @@ int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_
     f.ld = out_row_stride;
     int rc = engine->span_begin(st, 2);
     if (rc != SPADE_OK) return rc;
-    const dim3 grid((unsigned)((G + 255) / 256), (unsigned)((rows + kExpandRows - 1) / kExpandRows));
-    k_expand<<<grid, 256, 0, st>>>(f, (const unsigned long long *)raw, raw_row_stride, engine->offsets.p, rows);
-    CUDA_TRY(cudaGetLastError());
+    const int64_t rows_per_launch = (int64_t)65535 * kExpandRows;        // gridDim.y limit
+    for (int64_t r0 = 0; r0 < rows; r0 += rows_per_launch) {
+        const int64_t nr = std::min(rows_per_launch, rows - r0);
+        FinCtx fr = f;
+        if (fr.up) fr.up += r0 * out_row_stride;
+        if (fr.down) fr.down += r0 * out_row_stride;
+        if (fr.fc) fr.fc += r0 * out_row_stride;
+        if (fr.cpm) fr.cpm += r0 * out_row_stride;
+        if (fr.k) fr.k += r0 * out_row_stride;
+        const dim3 grid((unsigned)((G + 255) / 256), (unsigned)((nr + kExpandRows - 1) / kExpandRows));
+        k_expand<<<grid, 256, 0, st>>>(fr, (const unsigned long long *)raw + r0 * raw_row_stride, raw_row_stride,
+                                       engine->offsets.p + r0, nr);
+        CUDA_TRY(cudaGetLastError());
+    }
     rc = engine->span_end(st);
     if (rc != SPADE_OK) return rc;
     engine->launches += 1;

@@ -98,17 +98,23 @@ class PeerTables:
         self.ptr = {}
         handles = [None]
         if rank == 0:
-            hs = {}
-            for name in self.names:
-                p = ctypes.c_void_p()
-                self._ok(self._lib.spade_device_alloc(device, ctypes.byref(p),
-                                                      self.rows * self.cols * self.ITEM[name]))
-                buf = ctypes.create_string_buffer(64)
-                self._ok(self._lib.spade_ipc_export(device, p, buf))
-                self.ptr[name] = p.value
-                hs[name] = bytes(buf.raw)
-            handles = [hs]
+            try:
+                hs = {}
+                for name in self.names:
+                    p = ctypes.c_void_p()
+                    self._ok(self._lib.spade_device_alloc(device, ctypes.byref(p),
+                                                          self.rows * self.cols * self.ITEM[name]))
+                    self.ptr[name] = p.value
+                    buf = ctypes.create_string_buffer(64)
+                    self._ok(self._lib.spade_ipc_export(device, p, buf))
+                    hs[name] = bytes(buf.raw)
+                handles = [hs]
+            except RuntimeError as exc:                # every rank must leave the broadcast together
+                handles = [str(exc)]
         dist.broadcast_object_list(handles, src=0)
+        if isinstance(handles[0], str):
+            self.close()
+            raise RuntimeError(handles[0])
         if rank != 0:
             for name in self.names:
                 p = ctypes.c_void_p()
