@@ -100,6 +100,10 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }                 // temporaries on error paths do not leak
     cudaError_t reserve(size_t count)
     {
         if (count <= cap && p) return cudaSuccess;

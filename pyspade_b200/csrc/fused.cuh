@@ -20,26 +20,11 @@ namespace spade {
 #ifndef SPADE_MIN_CTAS
 #define SPADE_MIN_CTAS 6
 #endif
-#ifndef SPADE_PIPELINE
-#define SPADE_PIPELINE 0
-#endif
-#ifndef SPADE_LOAD
-#define SPADE_LOAD 1
-#endif
 // Streaming 64-bit load of layout data.  The kernel keeps almost all of the SM's 228 KB as
-// shared memory, so L1 has only a few hundred lines: loads that allocate there (ld.global.nc)
-// stall once more lines are pending than exist.  ld.global.cg goes through L2 only.
+// shared memory, so L1 has only a few hundred lines; ld.global.cg goes through L2 only.
 __device__ __forceinline__ unsigned long long stream_load(const unsigned long long *p)
 {
-#if SPADE_LOAD == 0
-    return __ldg(p);
-#elif SPADE_LOAD == 1
     return __ldcg(p);
-#else
-    unsigned long long v;
-    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-#endif
 }
 
 constexpr int kWarpsPerCta = 4;
@@ -175,9 +160,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     const uint32_t head = dense ? kDenseLanes : 0;
     unsigned long long dacc = 0ull;
 
-    // Software pipeline over batches of kMemberBatch member cells: the loads of batch i+1 are
-    // in flight while batch i is added into the accumulators.  Member ids and their segment
-    // bounds are fetched 32 members at a time, one group ahead (two register sets by parity).
+    // Batches of kMemberBatch member cells: all segment loads of a batch are issued, then the
+    // batch is added into the accumulators cell by cell.  Member ids and their segment bounds
+    // are fetched 32 members at a time, one group ahead (two register sets by parity).
+    // (Keeping a second batch in flight in registers was measured slower: the SM is bound by
+    // the LSU data pipe, not by latency.)
     uint32_t mb[2] = {0, 0}, me[2] = {0, 0};
     auto fetch_meta = [&](int grp, uint32_t &b, uint32_t &e) {
         b = 0; e = 0;                                  // b == e == 0: no member in this lane
@@ -256,23 +243,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     const int nb = (cntm + kMemberBatch - 1) / kMemberBatch;
     if (nb > 0) {
         fetch_meta(0, mb[0], me[0]);
-#if SPADE_PIPELINE
-        Batch A, B;
-        load(A, 0);
-        for (int ib = 0; ib < nb; ib += 2) {
-            if (ib + 1 < nb) load(B, ib + 1);
-            process(A);
-            if (ib + 1 >= nb) break;
-            if (ib + 2 < nb) load(A, ib + 2);
-            process(B);
-        }
-#else
         Batch A;
         for (int ib = 0; ib < nb; ++ib) {
             load(A, ib);
             process(A);
         }
-#endif
     }
     if (dense) {                   // hand the register accumulators to the common finalize
         const int32_t dg = a.dgene[p * kDenseLanes + lane];
