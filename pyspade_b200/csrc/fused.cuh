@@ -295,7 +295,39 @@ k_finalize_split(const FinCtx f, const unsigned long long *__restrict__ gsum,
                   1.0 / (double)((long long)f.M - N));
 }
 
-// After the segmented sort a duplicated cell index inside a set sits next to its twin.
+// Member cells of every set in ascending order (copy): one CTA per set, bitonic sort in shared
+// memory, sets of up to kSortMax cells.  Order inside a set does not change any sum; sorted
+// walks make the warps that work on one gene partition sweep the cells in step (L2 reuse).
+constexpr int kSortMax = 8192;
+constexpr int kSortThreads = 256;
+
+__global__ void __launch_bounds__(kSortThreads)
+k_sort_members(const int32_t *__restrict__ members, const int64_t *__restrict__ offsets,
+               int32_t *__restrict__ sorted)
+{
+    extern __shared__ int32_t keys[];
+    const int64_t beg = offsets[blockIdx.x];
+    const int n = (int)(offsets[blockIdx.x + 1] - beg);
+    if (n <= 0) return;
+    int m = 32;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) keys[i] = i < n ? members[beg + i] : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int32_t a = keys[i], b = keys[l];
+                    if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted[beg + i] = keys[i];
+}
+
+// After the sort a duplicated cell index inside a set sits next to its twin.
 __global__ void k_check_duplicates(const int32_t *__restrict__ sorted, const int64_t *__restrict__ offsets,
                                    int64_t S, int64_t total, int *__restrict__ err)
 {

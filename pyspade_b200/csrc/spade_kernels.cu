@@ -364,7 +364,7 @@ struct spade_engine {
     }
 
     // Tail table for a batch whose sets all have N members: window of plausible k per gene
-    // (mean +- 8 sd + 8, clipped to the support) computed on the host from n_g, entries filled
+    // (mean +- 6 sd + 6, clipped to the support; a k outside it is evaluated directly) computed on the host from n_g, entries filled
     // on the device by hyper_tails itself.  *built = false when the table would be too large.
     int build_tail_table(int64_t N, cudaStream_t st, bool *built)
     {
@@ -383,7 +383,7 @@ struct spade_engine {
                 const double pr = (double)ng / M;
                 const double mu = (double)N * pr;
                 const double var = C > 1 ? (double)N * pr * (1.0 - pr) * (M - (double)N) / (M - 1.0) : 0.0;
-                const double w = 8.0 * std::sqrt(std::max(var, 0.0)) + 8.0;
+                const double w = 6.0 * std::sqrt(std::max(var, 0.0)) + 6.0;
                 const int64_t a = std::max<int64_t>(N - (C - ng), 0), b = std::min<int64_t>(ng, N);
                 const int64_t lo = std::max<int64_t>(a, (int64_t)std::floor(mu - w));
                 const int64_t hi = std::min<int64_t>(b, (int64_t)std::ceil(mu + w));
@@ -702,12 +702,23 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
     // other sets that contain the cell ask for it.  Order inside a set does not change any sum.
     if (engine->sort_members && total > 1) {
         CUDA_TRY(engine->members_sorted.reserve(total));
-        size_t tb = 0;
-        CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(nullptr, tb, d_members, engine->members_sorted.p, total, S,
-                                                    engine->offsets.p, engine->offsets.p + 1, st));
-        CUDA_TRY(engine->sort_temp.reserve(tb));
-        CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(engine->sort_temp.p, tb, d_members, engine->members_sorted.p,
-                                                    total, S, engine->offsets.p, engine->offsets.p + 1, st));
+        int64_t maxN = 0;
+        for (int64_t s = 0; s < S; ++s) maxN = std::max(maxN, offsets[s + 1] - offsets[s]);
+        if (maxN <= kSortMax) {
+            int m = 32;
+            while (m < maxN) m <<= 1;
+            k_sort_members<<<(unsigned)S, kSortThreads, m * sizeof(int32_t), st>>>(d_members, engine->offsets.p,
+                                                                                engine->members_sorted.p);
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            // very large sets: CUB's segmented sort (it synchronises the stream internally)
+            size_t tb = 0;
+            CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(nullptr, tb, d_members, engine->members_sorted.p, total, S,
+                                                        engine->offsets.p, engine->offsets.p + 1, st));
+            CUDA_TRY(engine->sort_temp.reserve(tb));
+            CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(engine->sort_temp.p, tb, d_members, engine->members_sorted.p,
+                                                        total, S, engine->offsets.p, engine->offsets.p + 1, st));
+        }
         d_members = engine->members_sorted.p;
         k_check_duplicates<<<grid_for(total, 256), 256, 0, st>>>(d_members, engine->offsets.p, S, total, engine->err.p);
         CUDA_TRY(cudaGetLastError());
