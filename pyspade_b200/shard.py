@@ -160,11 +160,13 @@ class SharedHostTables:
     strided views of its own rows to ``Engine.run(..., row_stride=...)``: every GPU then
     delivers its rows over its own PCIe link, in parallel, and rank 0 reads the complete
     tables from the same mapping after a barrier.  No GPU-to-GPU traffic at all - the right
-    path when the tables are wanted on the host (file writers, the e2e benchmark)."""
+    path when the tables are wanted on the host (file writers, the e2e benchmark).
+    ``touch=(first_row, row_step, count)``: the rows this rank will write, zero-filled by it
+    before the tables are pinned (NUMA first touch)."""
 
     DTYPE = {"up": np.float64, "down": np.float64, "fc": np.float64, "cpm": np.float64, "k": np.int32}
 
-    def __init__(self, names, rows, cols, rank, world_size, pin=True, directory="/dev/shm"):
+    def __init__(self, names, rows, cols, rank, world_size, pin=True, directory="/dev/shm", touch=None):
         import torch.distributed as dist
 
         from . import _lib
@@ -192,6 +194,13 @@ class SharedHostTables:
             for n in self.names:
                 self.arrays[n] = np.memmap(self.paths[n], dtype=self.DTYPE[n], mode="r+",
                                            shape=(self.rows, self.cols))
+        if touch is not None:
+            # first touch: a rank's own rows get their pages from the memory node the rank runs
+            # on, instead of all tables landing on the node of whoever pins them first
+            first_row, row_step, count = touch
+            for n in self.names:
+                self.rows_view(n, first_row, row_step, count)[:] = 0
+            dist.barrier()
         if pin:
             for n in self.names:
                 a = self.arrays[n]
@@ -216,7 +225,7 @@ class SharedHostTables:
 _SHARED = {}
 
 
-def _shared_tables(names, rows, cols, rank, world_size):
+def _shared_tables(names, rows, cols, rank, world_size, touch=None):
     """One set of shared host tables per (names, cols), grown when more rows are needed."""
     key = (tuple(names), cols)
     cur = _SHARED.get(key)
@@ -224,7 +233,7 @@ def _shared_tables(names, rows, cols, rank, world_size):
         return cur
     if cur is not None:
         cur.close()
-    _SHARED[key] = SharedHostTables(names, rows, cols, rank, world_size)
+    _SHARED[key] = SharedHostTables(names, rows, cols, rank, world_size, touch=touch)
     return _SHARED[key]
 
 
@@ -256,8 +265,12 @@ def run_sharded(engine, sets, tables=("up", "down", "fc", "cpm"), balance=False,
     S, G = len(sets), engine.G
 
     if gather == "host":
+        if balance:
+            touch = (int(sum(len(a) for a in assignment[:rank])), 1, len(mine))
+        else:
+            touch = (rank, P, len(mine))
         try:
-            shared = _shared_tables(names, S, G, rank, P)
+            shared = _shared_tables(names, S, G, rank, P, touch=touch)
         except MemoryError:
             gather = "nccl"
     if gather == "host":
