@@ -270,7 +270,7 @@ def main():
         # every rank (CUDA IPC).  A peer's test kernel stores its 8-byte words straight into rank
         # 0's memory over NVLink while it computes (3x fewer bytes than the three float64
         # tables); rank 0 writes its own rows directly and finishes the peers' rows with
-        # k_expand (set i of rank r = row i*world + r of the final tables).
+        # k_expand; rank 0 takes a smaller share of the draws to make up for that work.
         # Fallback: one NCCL gather per table.
         from pyspade_b200 import shard
         ok = torch.ones(1, device=dev)
@@ -297,23 +297,54 @@ def main():
                             for k in TABLES}
     step_flag = torch.zeros(1, device=dev)
     final = None
-    if peer is not None and rank == 0:
-        final = {k: torch.empty((S * world, G), dtype=torch.float64, device=dev) for k in TABLES}
-    peer_sizes = np.full(S, N, dtype=np.int64)
+    batches_dev = batches
+    if peer is not None:
+        # rank 0 also expands everybody else's words: it takes a smaller share of the draws so
+        # that all ranks finish together (shares are contiguous blocks of the global draw list:
+        # rank r's sets are rows first[r] .. first[r] + share[r] - 1 of the tables on rank 0)
+        share = shard.expander_shares(S * world, world)
+        first = [int(sum(share[:r])) for r in range(world)]
+        batches_dev = []
+        for b in range(n_batches):
+            mine = all_draws[b * S * world + first[rank]: b * S * world + first[rank] + share[rank]]
+            members, offsets = synth.concat_sets(mine)
+            batches_dev.append((mine, members, offsets, torch.from_numpy(members).to(dev)))
+        if rank == 0:
+            final = {k: torch.empty((S * world, G), dtype=torch.float64, device=dev) for k in TABLES}
+            peer_sizes = np.full(S * world - share[0], N, dtype=np.int64)
     step_no = [0]
 
+    side = torch.cuda.Stream(device=dev) if (peer is not None and rank == 0) else None
+    expanded = [None]                       # event: the previous step's expansion has finished
+
     def step_peer(dmem, offsets):
-        buf = peer[step_no[0] & 1]          # peers fill one buffer while rank 0 expands the other
+        # Peers fill one word buffer while rank 0 expands the other.  Rank 0 expands step i on a
+        # side stream while its main stream already computes step i+1 (the test kernel is bound
+        # by the LSU data pipe, the expansion by memory); the expansion of step i has to finish
+        # before rank 0 releases the peers into step i+2 (they reuse its word buffer) - i.e.
+        # before rank 0 enters the all-reduce of step i+1.
+        buf = peer[step_no[0] & 1]
         step_no[0] += 1
         if rank == 0:
-            eng.run_device(dmem, offsets, {k: final[k].data_ptr() for k in TABLES}, row_stride=world * G)
+            main = torch.cuda.current_stream(dev)
+            eng.run_device(dmem, offsets, {k: final[k][:share[0]] for k in TABLES})     # rank 0's own rows
+            if expanded[0] is not None:
+                main.wait_event(expanded[0])
             dist.all_reduce(step_flag)      # passes once every peer's words have landed
-            for r in range(1, world):
-                eng.expand(buf.address("raw", first_row=r * S), peer_sizes,
-                           {k: final[k].data_ptr() + 8 * r * G for k in TABLES}, row_stride=world * G)
+            landed = torch.cuda.Event()
+            landed.record(main)
+            side.wait_event(landed)
+            eng.expand(buf.address("raw", first_row=share[0]), peer_sizes,
+                       {k: final[k].data_ptr() + 8 * share[0] * G for k in TABLES}, stream=side)
+            expanded[0] = torch.cuda.Event()
+            expanded[0].record(side)
         else:
-            eng.run_raw(dmem, offsets, buf.address("raw", first_row=rank * S))
+            eng.run_raw(dmem, offsets, buf.address("raw", first_row=first[rank]))
             dist.all_reduce(step_flag)
+
+    def drain_peer():
+        if side is not None and expanded[0] is not None:
+            torch.cuda.current_stream(dev).wait_event(expanded[0])
 
     def gather_tables():
         if world == 1:
@@ -322,7 +353,7 @@ def main():
             dist.gather(out_dev[k], gathered[k] if rank == 0 else None, dst=0)
 
     def step_device(i):
-        _, _, offsets, dmem = batches[i % n_batches]
+        _, _, offsets, dmem = batches_dev[i % n_batches]
         if peer is not None:
             step_peer(dmem, offsets)
         else:
@@ -363,7 +394,10 @@ def main():
             return
         dmem = torch.from_numpy(members).to(dev, non_blocking=True)          # H2D of the index lists
         if peer is not None:
+            _, members, offsets, _ = batches_dev[i % n_batches]
+            dmem = torch.from_numpy(members).to(dev, non_blocking=True)
             step_peer(dmem, offsets)
+            drain_peer()
             if rank == 0:
                 for k in TABLES:
                     host_out_t[k].copy_(final[k], non_blocking=True)
@@ -390,6 +424,7 @@ def main():
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        drain_peer()                        # N > 1: rank 0's last expansion belongs to the timed region
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -418,7 +453,8 @@ def main():
     # roofline of the dominant kernel (per rank; rank 0's kernel times)
     peak, peak_src = peaks()
     launches_per_step = 1                      # one fused launch per step (+ the tail-table fill)
-    gather_bytes, path_bytes = algorithmic_bytes(rho, [N] * S, C, G, B_OUT)
+    sets_rank0 = share[0] if peer is not None else S          # rank 0's kernel times are reported
+    gather_bytes, path_bytes = algorithmic_bytes(rho, [N] * sets_rank0, C, G, B_OUT)
     test_ms = kt["test_ms"] / args.steps
     table_ms = kt["table_ms"] / args.steps
     achieved = path_bytes / (test_ms * 1e-3) / 1e9
@@ -431,8 +467,8 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": path_bytes / launches_per_step,
                 "launch_ms": test_ms / launches_per_step, "launches_per_step": launches_per_step,
-                "bytes_per_test": path_bytes / (S * G), "gather_bytes_per_launch": gather_bytes,
-                "tail_table_ms_per_step": table_ms}
+                "bytes_per_test": path_bytes / (sets_rank0 * G), "gather_bytes_per_launch": gather_bytes,
+                "sets_per_launch": sets_rank0, "other_kernels_ms_per_step": table_ms}
 
     line = None
     if rank == 0:
@@ -444,6 +480,7 @@ def main():
                            "cells": C, "genes": G, "draws_per_gpu": S, "set_size": N, "nnz": nnz,
                            "density": rho, "sharding": f"draws round-robin over {world} rank(s), matrix replicated",
                            "gather": gather_mode,
+                           "draws_per_rank": (share if peer is not None else [S] * world),
                            "l2": "inputs larger than L2: 1.0 GB cell-major matrix read + 0.8 GB of tables written per step",
                            "stage_seconds": stage_s},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "path": e2e_mode,
@@ -485,17 +522,18 @@ def main():
     # rows that rank stored into rank 0's tables
     if world > 1 and peer is not None:
         step_device(0)
+        drain_peer()
         torch.cuda.synchronize()
         dist.barrier()
         if rank == 0:
             other = world - 1
-            theirs = all_draws[other: S * world: world][:4]
+            theirs = all_draws[first[other]: first[other] + 4]
             m2, o2 = synth.concat_sets(theirs)
             chk = {k: torch.empty((4, G), dtype=torch.float64, device=dev) for k in TABLES}
             eng.run_device(torch.from_numpy(m2).to(dev), o2, chk)
             torch.cuda.synchronize()
             same = all(bool(torch.equal(chk[k].view(torch.int64),
-                                        final[k][other::world][:4].view(torch.int64))) for k in TABLES)
+                                        final[k][first[other]: first[other] + 4].view(torch.int64))) for k in TABLES)
             line["multi_gpu_check"] = {"rows_of_rank": other, "sets": 4, "bit_identical": same}
         dist.barrier()
     if rank == 0:

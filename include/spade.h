@@ -168,6 +168,10 @@ int spade_run_strided(spade_engine *engine, const int32_t *members, int members_
  * (device memory, possibly a peer GPU's).  spade_expand, on an engine staged from the same
  * matrix with the same background, turns rows of such words into the tables - bit-identical to
  * what spade_run would have written.  set_sizes: host int64[rows], N of every row's set.
+ * spade_expand may run on another stream than the spade_run calls of the same engine: it
+ * reuses the tail table the last spade_run built when that fits its set size, and that
+ * table is not overwritten by the next spade_run (two tables are used in turn) - it must only
+ * have finished before the spade_run after the next one starts.
  * Sets above SPADE_OPT_MEMBER_BLOCK cells are refused by the raw form.
  */
 int spade_run_raw(spade_engine *engine, const int32_t *members, int members_location,
@@ -190,8 +194,9 @@ int spade_ipc_open(int device, const unsigned char handle[64], void **dptr);
 int spade_ipc_close(int device, void *dptr);
 
 /* Kernel-time accounting (CUDA events on the launch streams, accumulated since the last
- * reset).  test_ms = the fused test kernel (member accumulation + tails + table writes;
- * plus the split-path finalize), table_ms = tail-table builds.  Synchronises.
+ * reset).  test_ms = the fused test kernel (member accumulation + tails + table writes),
+ * table_ms = everything else spade_run / spade_expand launch (tail-table builds, split-path
+ * finalize, expansion of raw words).  Synchronises.
  * launches = kernels launched by spade_run. */
 int spade_timing(spade_engine *engine, double *test_ms, double *table_ms, int64_t *launches,
                  int reset);

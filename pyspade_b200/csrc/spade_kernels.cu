@@ -101,8 +101,11 @@ struct spade_engine {
     DevBuf<int32_t> members, members_sorted;
     DevBuf<uint8_t> sort_temp;
     DevBuf<int64_t> offsets;
-    DevBuf<TabMeta> tmeta;
-    DevBuf<double2> tab;
+    // Tail table, two copies used in turn: a table stays untouched while the NEXT one is built,
+    // so work still reading it on another stream (spade_expand of the previous batch) is safe.
+    DevBuf<TabMeta> tmeta_buf[2];
+    DevBuf<double2> tab_buf[2];
+    int tab_cur = 0;
     DevBuf<int32_t> blk_row, blk_cnt;
     DevBuf<int64_t> blk_off;
     DevBuf<unsigned long long> gsum;
@@ -115,7 +118,8 @@ struct spade_engine {
     int64_t tab_N = -1;                // set size the tail table on the device was built for
     int64_t tab_epoch = -1, bg_epoch = 0;
     PinnedBuf<TabMeta> h_tmeta;
-    PinnedBuf<int64_t> h_offsets;
+    PinnedBuf<int64_t> h_offsets, h_sizes;
+    DevBuf<int64_t> sizes;             // spade_expand's own upload buffers (it may run on another stream)
 
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> ev_pool;
@@ -158,7 +162,7 @@ struct spade_engine {
             float ms = 0.f;
             CUDA_TRY(cudaEventSynchronize(s.b));
             CUDA_TRY(cudaEventElapsedTime(&ms, s.a, s.b));
-            (s.kind == 1 ? table_ms : test_ms) += ms;
+            (s.kind == 0 ? test_ms : table_ms) += ms;
         }
         spans.clear();
         ev_used = 0;
@@ -396,6 +400,9 @@ struct spade_engine {
             total += (unsigned long long)t.len;
         }
         if (total > (unsigned long long)kMaxTableEntries) return SPADE_OK;
+        tab_cur ^= 1;
+        DevBuf<TabMeta> &tmeta = tmeta_buf[tab_cur];
+        DevBuf<double2> &tab = tab_buf[tab_cur];
         CUDA_TRY(tmeta.reserve(G));
         CUDA_TRY(tab.reserve(total));
         CUDA_TRY(h_tmeta.upload(tmeta.p, (size_t)G, st));
@@ -439,12 +446,15 @@ struct spade_engine {
         seg.release(); dslot.release(); dgene.release(); dense_on.release();
         ent.release(); median.release(); lf.release(); n.release(); meta.release(); ncmask.release();
         err.release(); members.release(); members_sorted.release(); sort_temp.release();
-        offsets.release(); tmeta.release(); tab.release();
+        offsets.release();
+        for (int i = 0; i < 2; ++i) { tmeta_buf[i].release(); tab_buf[i].release(); }
         blk_row.release(); blk_cnt.release(); blk_off.release(); gsum.release(); gcnt.release();
         for (int b = 0; b < 4; ++b) out_f64[b].release();
         out_k.release();
         h_tmeta.release();
         h_offsets.release();
+        h_sizes.release();
+        sizes.release();
         for (int i = 0; i < 2; ++i) {
             if (work[i]) cudaStreamDestroy(work[i]);
             work[i] = nullptr;
@@ -782,8 +792,8 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
         a.fin.M = (int)C;
         a.fin.nc_mode = engine->n_nc > 0;
         a.fin.meta = engine->meta.p;
-        a.fin.tmeta = table ? engine->tmeta.p : nullptr;
-        a.fin.tab = table ? engine->tab.p : nullptr;
+        a.fin.tmeta = table ? engine->tmeta_buf[engine->tab_cur].p : nullptr;
+        a.fin.tab = table ? engine->tab_buf[engine->tab_cur].p : nullptr;
         a.fin.lf = engine->lf.p;
         a.fin.ld = host_out ? G : out_row_stride;
         if (host_out) {
@@ -952,10 +962,10 @@ int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_
         if (set_sizes[r] < 0 || set_sizes[r] > engine->C) { set_error("set size out of range"); return SPADE_ERR_ARG; }
         uniform &= set_sizes[r] == set_sizes[0];
     }
-    CUDA_TRY(engine->offsets.reserve(rows));
-    CUDA_TRY(engine->h_offsets.reserve(rows));
-    memcpy(engine->h_offsets.p, set_sizes, rows * sizeof(int64_t));
-    CUDA_TRY(engine->h_offsets.upload(engine->offsets.p, (size_t)rows, st));
+    CUDA_TRY(engine->sizes.reserve(rows));
+    CUDA_TRY(engine->h_sizes.reserve(rows));
+    memcpy(engine->h_sizes.p, set_sizes, rows * sizeof(int64_t));
+    CUDA_TRY(engine->h_sizes.upload(engine->sizes.p, (size_t)rows, st));
     bool table = false;
     if (uniform && set_sizes[0] > 0 && (engine->tail_mode == 2 || (engine->tail_mode == 1 && rows >= 32))) {
         if (engine->tab_N == set_sizes[0] && engine->tab_epoch == engine->bg_epoch) {
@@ -970,8 +980,8 @@ int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_
     f.M = (int)engine->C;
     f.nc_mode = engine->n_nc > 0;
     f.meta = engine->meta.p;
-    f.tmeta = table ? engine->tmeta.p : nullptr;
-    f.tab = table ? engine->tab.p : nullptr;
+    f.tmeta = table ? engine->tmeta_buf[engine->tab_cur].p : nullptr;
+    f.tab = table ? engine->tab_buf[engine->tab_cur].p : nullptr;
     f.lf = engine->lf.p;
     f.up = up; f.down = down; f.fc = fc; f.cpm = cpm; f.k = k;
     f.ld = out_row_stride;
@@ -988,7 +998,7 @@ int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_
         if (fr.k) fr.k += r0 * out_row_stride;
         const dim3 grid((unsigned)((G + 255) / 256), (unsigned)((nr + kExpandRows - 1) / kExpandRows));
         k_expand<<<grid, 256, 0, st>>>(fr, (const unsigned long long *)raw + r0 * raw_row_stride, raw_row_stride,
-                                       engine->offsets.p + r0, nr);
+                                       engine->sizes.p + r0, nr);
         CUDA_TRY(cudaGetLastError());
     }
     rc = engine->span_end(st);

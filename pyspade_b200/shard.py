@@ -40,6 +40,24 @@ def plan(sizes, world_size, balance=False):
     return [np.flatnonzero(owner == r).astype(np.int64) for r in range(world_size)]
 
 
+def expander_shares(total_sets, world_size, expand_cost=0.12):
+    """Contiguous shares of ``total_sets`` for the raw-word gather, where rank 0 also expands
+    the words of all other ranks (``spade_expand``, about ``expand_cost`` of the cost of
+    testing a set): rank 0 takes fewer sets so that every rank finishes together,
+        x (1 - e) + T e = (T - x) / (P - 1),   T = total_sets, e = expand_cost.
+    Returns ``counts`` (list, rank 0 first); the ranks > 0 get equal counts."""
+    P, T, e = world_size, total_sets, expand_cost
+    if P <= 1:
+        return [T]
+    x = T * (1.0 / (P - 1) - e) / (1.0 - e + 1.0 / (P - 1))
+    y = int(np.ceil((T - max(x, 0.0)) / (P - 1)))
+    x = T - y * (P - 1)
+    while x < 0:                                       # tiny T: give the remainder to the peers
+        y -= 1
+        x = T - y * (P - 1)
+    return [x] + [y] * (P - 1)
+
+
 def gather_rows(local, assignment, rank, world_size, n_cols, group=None):
     """Gather per-rank tables to rank 0 and put the rows back in global set order.
 
