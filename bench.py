@@ -367,7 +367,8 @@ def main():
     if world > 1:
         from pyspade_b200 import shard
         try:
-            shared = shard.SharedHostTables(TABLES, S * world, G, rank, world, touch=(rank, world, S))
+            shared = shard.SharedHostTables(TABLES, S * world, G, rank, world, touch=(rank, world, S),
+                                            device=local_rank)
             e2e_mode = ("Engine.run on every rank into host tables shared by the node "
                         "(POSIX shm, page-locked; rows interleaved by rank)")
         except Exception as exc:                                       # noqa: BLE001

@@ -172,6 +172,37 @@ class PeerTables:
         self.ptr = {}
 
 
+class _near_gpu:
+    """Context manager: run the calling thread on the CPUs NVML reports as local to GPU
+    ``device`` (so that first-touched pages come from that GPU's memory node), then restore the
+    previous affinity.  A no-op when NVML or the affinity calls are unavailable."""
+
+    def __init__(self, device):
+        self.device, self.saved = device, None
+
+    def __enter__(self):
+        if self.device is None:
+            return self
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[self.device]) if visible else self.device
+            self.saved = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        except Exception:                                  # noqa: BLE001 - best effort only
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except OSError:
+                pass
+        return False
+
+
 class SharedHostTables:
     """Result tables in host memory shared by the ranks of one node (POSIX shared memory,
     ``/dev/shm``), page-locked in every rank (``spade_host_register``).  Each rank hands
@@ -180,11 +211,13 @@ class SharedHostTables:
     tables from the same mapping after a barrier.  No GPU-to-GPU traffic at all - the right
     path when the tables are wanted on the host (file writers, the e2e benchmark).
     ``touch=(first_row, row_step, count)``: the rows this rank will write, zero-filled by it
-    before the tables are pinned (NUMA first touch)."""
+    before the tables are pinned (NUMA first touch; with ``device`` the thread is moved to the
+    CPUs next to that GPU while it does so)."""
 
     DTYPE = {"up": np.float64, "down": np.float64, "fc": np.float64, "cpm": np.float64, "k": np.int32}
 
-    def __init__(self, names, rows, cols, rank, world_size, pin=True, directory="/dev/shm", touch=None):
+    def __init__(self, names, rows, cols, rank, world_size, pin=True, directory="/dev/shm", touch=None,
+                 device=None):
         import torch.distributed as dist
 
         from . import _lib
@@ -216,8 +249,9 @@ class SharedHostTables:
             # first touch: a rank's own rows get their pages from the memory node the rank runs
             # on, instead of all tables landing on the node of whoever pins them first
             first_row, row_step, count = touch
-            for n in self.names:
-                self.rows_view(n, first_row, row_step, count)[:] = 0
+            with _near_gpu(device):
+                for n in self.names:
+                    self.rows_view(n, first_row, row_step, count)[:] = 0
             dist.barrier()
         if pin:
             for n in self.names:
@@ -251,7 +285,7 @@ def _shared_tables(names, rows, cols, rank, world_size, touch=None):
         return cur
     if cur is not None:
         cur.close()
-    _SHARED[key] = SharedHostTables(names, rows, cols, rank, world_size, touch=touch)
+    _SHARED[key] = SharedHostTables(names, rows, cols, rank, world_size, touch=touch, device=world()[1])
     return _SHARED[key]
 
 
