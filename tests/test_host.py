@@ -275,3 +275,17 @@ def test_mat_writers_load_like_scipy_written_files(tmp_path):
             assert np.array_equal(m.data, r.data, equal_nan=True)
     spio.save_draw_tables([(str(tmp_path / "p1"), t), (str(tmp_path / "p2"), -t)])
     assert np.array_equal(np.asarray(sio.loadmat(str(tmp_path / "p2"))["matrix"].todense()), -t + 0.0, equal_nan=True)
+
+
+def test_expander_shares_balance_and_cover():
+    """Rank 0 expands everybody's raw words (cost e per set): x(1-e) + T e = (T - x)/(P - 1)."""
+    assert shard.expander_shares(1000, 1) == [1000]
+    for P in (2, 3, 4, 8):
+        T = 1000 * P
+        c = shard.expander_shares(T, P, expand_cost=0.12)
+        assert sum(c) == T and len(c) == P and min(c) >= 0 and len(set(c[1:])) == 1
+        rank0 = c[0] + 0.12 * (T - c[0])                # its own tests + the expansion of the others
+        assert abs(rank0 - c[1]) <= 2.0                  # finishes together with the peers
+    assert shard.expander_shares(3, 4) == [0, 1, 1, 1] and shard.expander_shares(0, 2) == [0, 0]
+    with shard._near_gpu(None):                          # no device: a no-op
+        pass
