@@ -267,3 +267,39 @@ if __name__ == "__main__":
     if "cli" in which:
         make_cli()
     print("golden fixtures written to", HERE)
+
+
+# --------------------------------------------------------------------------- cfg1_case.npz
+def make_cfg1():
+    """BASELINE.json configs[0]: DEobs on synthetic 2 000 cells x 5 000 genes, 10 regions of
+    30..200 cells - the reference's own CPU-runnable case.  Inputs come from the seeded
+    generators of pyspade_b200/synth.py (not stored); stored: the reference's perform_DE tables
+    (complement background) and perform_DE_NC tables (NC = every 50th cell) for all genes."""
+    from pyspade_b200 import synth
+    G, C, R = 5000, 2000, 10
+    counts = synth.counts_numpy(G, C, seed=0)
+    sets = synth.deobs_sets(C, R, lo=30, hi=200, uniform_int=True)
+    nc_idx = np.arange(0, C, 50)
+    df = pd.DataFrame.sparse.from_spmatrix(counts.astype(np.int32))
+    cpm = utils.cpm_normalization(df)
+    idx = np.arange(G)
+    out = {"nc_idx": nc_idx.astype(np.int64), "sizes": np.array([len(s) for s in sets])}
+    tabs = {m: np.zeros((4, R, G)) for m in ("complement", "nc")}
+    for s, members in enumerate(sets):
+        members = [int(v) for v in members]
+        N, up, down, fc, cp = utils.perform_DE(members, cpm, idx, os.cpu_count(), np.zeros(G), np.zeros(G),
+                                               np.ones(G), np.zeros(G))
+        tabs["complement"][:, s] = np.stack([up, down, fc, cp])
+        N, up, down, fc, cp = utils.perform_DE_NC(members, [int(v) for v in nc_idx], cpm, idx, os.cpu_count(),
+                                                  np.zeros(G), np.zeros(G), np.ones(G), np.zeros(G))
+        tabs["nc"][:, s] = np.stack([up, down, fc, cp])
+        print("region", s, "done", flush=True)
+    for mode in tabs:
+        for j, name in enumerate(("up", "down", "fc", "cpm")):
+            out[f"{mode}_{name}"] = tabs[mode][j]
+    np.savez_compressed(os.path.join(HERE, "cfg1_case.npz"), **out)
+
+
+if __name__ == "__main__" and "cfg1" in sys.argv[1:]:
+    make_cfg1()
+    print("cfg1_case.npz written")
