@@ -14,6 +14,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 via gpurun)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built library (``*.so`` is git-ignored): build it once, in-tree,
+    when nvcc is there, so that the suite does not depend on having run build() first."""
+    import shutil
+    try:
+        from pyspade_b200 import _build
+        if _build.needs_build() and shutil.which(os.environ.get("NVCC", "nvcc")):
+            _build.build()
+    except Exception as exc:                                   # noqa: BLE001 - tests will say why
+        print(f"[conftest] could not build libspade_b200: {exc}")
+
+
 def _has_gpu():
     try:
         import torch
