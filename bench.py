@@ -22,7 +22,8 @@ One "step" = one pass of the hot path over that batch: 33 M (gene, draw) tests p
             test) / its CUDA-event time, against the measured HBM copy bandwidth of
             MEASURED_PEAKS.json.
 ``cpu_baseline`` oracle per-gene port (oracle/de_port.py, kind "port": the Python reference
-            cannot travel to the GPU box) on a bounded sample of the same workload, all host
+            cannot travel to the GPU box; the port is ~8x faster per core than the reference
+            itself) on a bounded sample of the same workload, all host
             cores; the same sample is the parity check of the GPU tables (``parity``).
 """
 import argparse
