@@ -210,6 +210,22 @@ int spade_timing(spade_engine *engine, double *test_ms, double *table_ms, int64_
 int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_t *n,
                     const int64_t *N, int64_t count, double *logcdf, double *logsf);
 
+/*
+ * Gamma-fit tail of DErand for all genes at once (pySpade/DErand.py:250-292): per gene
+ * scipy.stats.gamma.fit of sign * table[:, g] over its finite values - the same start values
+ * (gamma_gen._fitstart, rv_continuous._fit_loc_scale_support), the same penalised negative
+ * log-likelihood and the same Nelder-Mead moves and stopping rule as scipy.optimize.fmin,
+ * restated in csrc/gamma_fit.cuh, one gene per thread.  table: float64 [S][ld] (host or
+ * device per table_location), the first G columns are used; sign = -1 for log p tables.
+ * Host outputs A, B, C (shape, loc, scale), float64[G], and optionally status int32[G]:
+ * 0 fitted, 1 skipped (<= 50 finite values; A = B = C = 0 as the reference leaves them),
+ * 2 all values equal (nan, 0, 1), 3 scipy would raise FitError (nan, nan, nan).
+ * Parameters agree with scipy's to the optimiser's own tolerance (1e-4) wherever its optimum
+ * is stable; see tests/test_gamma_fit.py.
+ */
+int spade_gamma_fit(int device, const double *table, int table_location, int64_t S, int64_t G,
+                    int64_t ld, double sign, double *A, double *B, double *C, int32_t *status);
+
 /* Page-locked host memory for result tables (fast device->host copies). */
 int spade_host_alloc(void **ptr, int64_t bytes);
 int spade_host_free(void *ptr);

@@ -42,7 +42,8 @@ def main(argv=None):
             norm=args.norm_method,
             RAND_M=args.randomization_method,
             background_cells=args.bg,
-            output_dir=args.output_dir)
+            output_dir=args.output_dir,
+            gamma_fit=args.gamma_fit)
         logger.info('Done.')
     else:
         logger.critical('Only the DEobs and DErand sub-commands are provided by this engine.')

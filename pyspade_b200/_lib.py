@@ -55,6 +55,9 @@ SIGNATURES = {
     "spade_hypergeom": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "spade_gamma_fit": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p]),
     "spade_host_alloc": (ctypes.c_int, [c_vpp, ctypes.c_int64]),
     "spade_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "spade_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),

@@ -33,6 +33,7 @@
 
 #include "common.cuh"
 #include "fused.cuh"
+#include "gamma_fit.cuh"
 #include "stage.cuh"
 #include "tails.cuh"
 
@@ -1127,6 +1128,60 @@ int spade_ipc_close(int device, void *dptr)
     return SPADE_OK;
 }
 #undef IPC_TRY
+
+namespace {
+// One gene per thread: the column walk is coalesced across the genes of a warp.
+__global__ void __launch_bounds__(128)
+k_gamma_fit(const double *__restrict__ tab, int S, int64_t G, int64_t ld, double sign, double *__restrict__ A,
+            double *__restrict__ B, double *__restrict__ C, int32_t *__restrict__ status)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    GammaColumn col{tab + g, ld, S, sign};
+    double out[3];
+    status[g] = gamma_fit_column(col, out);
+    A[g] = out[0];
+    B[g] = out[1];
+    C[g] = out[2];
+}
+}  // namespace
+
+int spade_gamma_fit(int device, const double *table, int table_location, int64_t S, int64_t G, int64_t ld,
+                    double sign, double *A, double *B, double *C, int32_t *status)
+{
+    auto fail = [&](int code, const std::string &m) { g_create_error = m; return code; };
+    if (S < 0 || G < 0 || ld < G || S > 0x7fffffff || (S > 0 && G > 0 && !table) || (G > 0 && (!A || !B || !C)))
+        return fail(SPADE_ERR_ARG, "bad table / output arguments");
+    if (table_location != SPADE_HOST && table_location != SPADE_DEVICE) return fail(SPADE_ERR_ARG, "bad location");
+    if (G == 0) return SPADE_OK;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return fail(SPADE_ERR_CUDA, cudaGetErrorString(ce));
+    DevBuf<double> dtab, dout;
+    DevBuf<int32_t> dst;
+#define G_TRY(expr)                                                                            \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return fail(SPADE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    const double *dt = table;
+    if (table_location == SPADE_HOST && S > 0) {
+        G_TRY(dtab.reserve((size_t)S * (size_t)G));
+        G_TRY(cudaMemcpy2D(dtab.p, G * sizeof(double), table, ld * sizeof(double), G * sizeof(double), S,
+                           cudaMemcpyHostToDevice));
+        dt = dtab.p;
+        ld = G;
+    }
+    G_TRY(dout.reserve(3 * (size_t)G));
+    G_TRY(dst.reserve((size_t)G));
+    k_gamma_fit<<<(unsigned)((G + 127) / 128), 128>>>(dt, (int)S, G, ld, sign, dout.p, dout.p + G, dout.p + 2 * G, dst.p);
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaMemcpy(A, dout.p, G * sizeof(double), cudaMemcpyDeviceToHost));
+    G_TRY(cudaMemcpy(B, dout.p + G, G * sizeof(double), cudaMemcpyDeviceToHost));
+    G_TRY(cudaMemcpy(C, dout.p + 2 * G, G * sizeof(double), cudaMemcpyDeviceToHost));
+    if (status) G_TRY(cudaMemcpy(status, dst.p, G * sizeof(int32_t), cudaMemcpyDeviceToHost));
+#undef G_TRY
+    return SPADE_OK;
+}
 
 int spade_host_alloc(void **ptr, int64_t bytes)
 {

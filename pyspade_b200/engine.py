@@ -353,3 +353,24 @@ def hypergeom_logcdf_logsf(k, M, n, N, device=0):
     if rc != _lib.SPADE_OK:
         raise SpadeError(f"spade_hypergeom failed ({rc}): {lib.spade_last_error(None).decode()}")
     return lc.reshape(shape), ls.reshape(shape)
+
+
+def gamma_fit(table, sign=-1.0, device=0):
+    """``spade_gamma_fit``: per-gene ``scipy.stats.gamma.fit`` of ``sign * table[:, g]`` (finite
+    values only) on the GPU.  ``table``: float64 ``[S, G]`` numpy array (or CUDA torch tensor).
+    Returns ``(A, B, C, status)``."""
+    lib = _lib.load()
+    if isinstance(table, np.ndarray):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        S, G = t.shape
+        ptr, loc = _ptr(t), _lib.SPADE_HOST
+    else:
+        assert table.is_cuda and table.is_contiguous() and table.dim() == 2
+        S, G = table.shape
+        ptr, loc = ctypes.c_void_p(table.data_ptr()), _lib.SPADE_DEVICE
+    A, B, C = np.zeros(G), np.zeros(G), np.zeros(G)
+    status = np.zeros(G, dtype=np.int32)
+    rc = lib.spade_gamma_fit(int(device), ptr, loc, S, G, G, float(sign), _ptr(A), _ptr(B), _ptr(C), _ptr(status))
+    if rc != _lib.SPADE_OK:
+        raise SpadeError(f"spade_gamma_fit failed ({rc}): {lib.spade_last_error(None).decode()}")
+    return A, B, C, status

@@ -76,5 +76,9 @@ def add_DErand_subparser(subparsers):
                         type=str, help='"equal" or "sgrna"')
     parser.add_argument("-b", "--bg", dest="bg", required=False, type=str, default="complement",
                         help="background cells: 'complement' or a key of the sgRNA dictionary")
+    parser.add_argument("--gamma_fit", dest="gamma_fit", required=False, type=str, default=None,
+                        choices=["scipy", "device"],
+                        help="not in the reference: 'scipy' (default) = the reference's per-gene "
+                             "scipy.stats.gamma.fit on the host cores, 'device' = the same procedure on the GPU")
     parser.add_argument("-o", "--output_dir", dest="output_dir", required=True,
                         help="output directory (must end with '/': the .npy names are concatenated)")

@@ -78,6 +78,11 @@ def main():
     res["gamma_fit_sample_genes"] = int(pick.size)
     res["gamma_fit_cores"] = os.cpu_count()
     res["gamma_fit_estimate_all_cores_s"] = dt / (2 * pick.size) * 2 * a.G / max(1, os.cpu_count())
+    # the same tail on the GPU (spade_gamma_fit), all genes, both directions
+    t0 = time.perf_counter()
+    DErand.gamma_parameters_device(got["up"], "up")
+    DErand.gamma_parameters_device(got["down"], "down")
+    res["gamma_fit_device_s"] = time.perf_counter() - t0
     print(json.dumps(res))
 
 
