@@ -205,7 +205,8 @@ int spade_timing(spade_engine *engine, double *test_ms, double *table_ms, int64_
  * K3 in isolation (parity probe): logcdf / logsf of scipy.stats.hypergeom for `count`
  * tuples (k, M, n, N) given as host int64 arrays, results to host float64 arrays.  Plain
  * scipy semantics (support clamps, nan for invalid shapes); the reference's
- * all([k, M, n, N]) guard of utils.py:212-213 is NOT applied here.
+ * all([k, M, n, N]) guard of utils.py:212-213 is NOT applied here.  M <= 2^27 (the probe
+ * builds a log-factorial table of M + 1 entries).
  */
 int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_t *n,
                     const int64_t *N, int64_t count, double *logcdf, double *logsf);

@@ -1039,7 +1039,7 @@ int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_
     if (ce != cudaSuccess) return fail(SPADE_ERR_CUDA, cudaGetErrorString(ce));
     int64_t maxM = 0;
     for (int64_t i = 0; i < count; ++i) {
-        if (M[i] > 0x7ffffff0ll) return fail(SPADE_ERR_ARG, "M too large");
+        if (M[i] > (int64_t(1) << 27)) return fail(SPADE_ERR_ARG, "M too large for the probe (limit 2^27)");
         maxM = std::max(maxM, M[i]);
     }
     std::vector<double> h(maxM + 1);
