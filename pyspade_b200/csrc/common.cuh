@@ -23,7 +23,11 @@ constexpr int kMaxGenesPerPart = 1 << kSlotBits;      // 8192
 // the 16-bit count field and the 47-bit sum budget (see stage.cuh) are sized for it.
 constexpr int kMemberBlock = 32768;
 constexpr int kSegAlign = 16;                         // entries: segments start on 128-byte lines
-constexpr int kDenseLanes = 32;                       // genes per partition kept in the dense block
+#ifndef SPADE_DENSE_REGS
+#define SPADE_DENSE_REGS 1
+#endif
+constexpr int kDenseRegs = SPADE_DENSE_REGS;          // register accumulators per lane for the dense head
+constexpr int kDenseLanes = 32 * kDenseRegs;          // genes per partition kept in the dense head
 
 struct __align__(16) GeneMeta {      // one per gene, fixed by the matrix and the background
     int32_t n;                       // #{cells : x <= cutoff}             (utils.py:200,211)

@@ -30,6 +30,8 @@ __device__ __forceinline__ unsigned long long stream_load(const unsigned long lo
 constexpr int kWarpsPerCta = 4;
 constexpr int kMemberBatch = SPADE_MEMBER_BATCH;   // member cells whose segments are in flight per warp
 constexpr int kIters = SPADE_ITERS;                // unrolled 32-entry steps per member segment
+static_assert(32 % kMemberBatch == 0, "a batch must not straddle two 32-member groups");
+// (SPADE_* macros: tuning variants built next to the product library, see _build.build(defines=...))
 
 struct FinCtx {
     int64_t G;
@@ -158,7 +160,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     // gene in a register, one aligned 256-byte read per member cell, no shared-memory traffic
     const bool dense = a.dense_on[p] != 0;
     const uint32_t head = dense ? kDenseLanes : 0;
-    unsigned long long dacc = 0ull;
+    unsigned long long dacc[kDenseRegs];
+#pragma unroll
+    for (int r = 0; r < kDenseRegs; ++r) dacc[r] = 0ull;
 
     // Batches of kMemberBatch member cells: all segment loads of a batch are issued, then the
     // batch is added into the accumulators cell by cell.  Member ids and their segment bounds
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     };
     struct Batch {
         uint32_t bb[kMemberBatch], ee[kMemberBatch];
-        unsigned long long r[kMemberBatch][kIters], dv[kMemberBatch];
+        unsigned long long r[kMemberBatch][kIters], dv[kMemberBatch][kDenseRegs];
     };
     constexpr int kBatchesPerGroup = 32 / kMemberBatch;
     auto load = [&](Batch &t, int ib) {
@@ -201,7 +205,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         for (int q = 0; q < kMemberBatch; ++q) {
             const uint2 se = mbuf[w + q];
             t.ee[q] = se.y;
-            t.dv[q] = (dense && se.y != 0) ? stream_load(ent + se.x + lane) : 0ull;
+#pragma unroll
+            for (int w2 = 0; w2 < kDenseRegs; ++w2)
+                t.dv[q][w2] = (dense && se.y != 0) ? stream_load(ent + se.x + lane + 32 * w2) : 0ull;
             t.bb[q] = se.x + head + lane;
         }
 #pragma unroll
@@ -236,7 +242,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
                 decode_entry(stream_load(ent + i), sl, ad);
                 acc[sl] += ad;
             }
-            dacc += t.dv[q];
+#pragma unroll
+            for (int w2 = 0; w2 < kDenseRegs; ++w2) dacc[w2] += t.dv[q][w2];
             __syncwarp();          // next cell may hit the same genes from other lanes
         }
     };
@@ -250,8 +257,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         }
     }
     if (dense) {                   // hand the register accumulators to the common finalize
-        const int32_t dg = a.dgene[p * kDenseLanes + lane];
-        if (dg >= 0) acc[dg - g0] = dacc;
+#pragma unroll
+        for (int w2 = 0; w2 < kDenseRegs; ++w2) {
+            const int32_t dg = a.dgene[p * kDenseLanes + lane + 32 * w2];
+            if (dg >= 0) acc[dg - g0] = dacc[w2];
+        }
         __syncwarp();
     }
 
