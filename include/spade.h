@@ -216,7 +216,7 @@ int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_
  * scipy.stats.gamma.fit of sign * table[:, g] over its finite values - the same start values
  * (gamma_gen._fitstart, rv_continuous._fit_loc_scale_support), the same penalised negative
  * log-likelihood and the same Nelder-Mead moves and stopping rule as scipy.optimize.fmin,
- * restated in csrc/gamma_fit.cuh, one gene per thread.  table: float64 [S][ld] (host or
+ * restated in csrc/gamma_fit.cuh, one gene per warp.  table: float64 [S][ld] (host or
  * device per table_location), the first G columns are used; sign = -1 for log p tables.
  * Host outputs A, B, C (shape, loc, scale), float64[G], and optionally status int32[G]:
  * 0 fitted, 1 skipped (<= 50 finite values; A = B = C = 0 as the reference leaves them),

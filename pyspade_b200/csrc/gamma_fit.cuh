@@ -5,9 +5,11 @@
 // data if needed), then scipy.optimize.fmin (Nelder-Mead, xtol = ftol = 1e-4, 600 iterations /
 // 600 evaluations) on rv_continuous._penalized_nnlf.  This file restates exactly that
 // procedure (same start values, same simplex moves, same penalty, same stopping rule) for one
-// gene per thread, so that the parameters agree with scipy's up to the sensitivity of the
-// simplex path to last-bit differences of log / lgamma.  The same source compiles for the
-// host (tests/gamma_host_harness.cpp) to be checked against scipy without a GPU.
+// gene, so that the parameters agree with scipy's up to the sensitivity of the simplex path to
+// last-bit differences of log / lgamma and of the summation order.  On the device one warp
+// owns one gene: the lanes split the draws of every likelihood evaluation and all lanes carry
+// the same simplex (WarpReduce); the same source compiles for the host with one "lane"
+// (SerialReduce, tests/gamma_host_harness.cpp) to be checked against scipy without a GPU.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -27,18 +29,57 @@ struct GammaColumn {                 // x_i = sign * tab[i * ld], non-finite val
     int64_t ld;
     int S;
     double sign;
+    int lane = 0, nlanes = 1;        // this caller walks i = lane, lane + nlanes, ...
 };
+
+struct SerialReduce {                // one caller sees every value
+    SPADE_HD double sum(double v) const { return v; }
+    SPADE_HD int sum(int v) const { return v; }
+    SPADE_HD double min(double v) const { return v; }
+    SPADE_HD double max(double v) const { return v; }
+};
+
+#ifdef __CUDACC__
+struct WarpReduce {                  // butterfly: every lane ends with the same bits
+    __device__ double sum(double v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ int sum(int v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ double min(double v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ double max(double v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+};
+#endif
 
 SPADE_HD inline bool gf_finite(double v) { return v - v == 0.0; }
 
 // rv_continuous._penalized_nnlf for the gamma distribution (theta = shape a, loc, scale).
-SPADE_HD inline double gamma_penalized_nnlf(const GammaColumn &c, int n, double a, double loc, double scale)
+template <class Reduce>
+SPADE_HD inline double gamma_penalized_nnlf(const GammaColumn &c, int n, double a, double loc, double scale,
+                                            const Reduce &red)
 {
     if (!(a > 0.0) || !(scale > 0.0)) return INFINITY;            // _argcheck, scale <= 0
     const double am1 = a - 1.0, lga = lgamma(a);
     double total = 0.0;
     int n_bad = 0;
-    for (int i = 0; i < c.S; ++i) {
+    for (int i = c.lane; i < c.S; i += c.nlanes) {
         const double x = c.sign * c.tab[(int64_t)i * c.ld];
         if (!gf_finite(x)) continue;
         const double y = (x - loc) / scale;
@@ -47,43 +88,47 @@ SPADE_HD inline double gamma_penalized_nnlf(const GammaColumn &c, int n, double 
         const double lp = xl - y - lga;
         if (gf_finite(lp)) total += lp; else ++n_bad;
     }
+    total = red.sum(total);
+    n_bad = red.sum(n_bad);
     return -total + (double)n_bad * kLogXMax100 + (double)n * log(scale);
 }
 
 // Status: 0 = fitted, 1 = skipped (<= 50 finite values: outputs untouched zeros),
 //         2 = all finite values equal -> (nan, 0, 1), 3 = scipy would raise FitError -> nan.
-SPADE_HD inline int gamma_fit_column(const GammaColumn &c, double out[3])
+template <class Reduce>
+SPADE_HD inline int gamma_fit_column(const GammaColumn &c, double out[3], const Reduce &red)
 {
     // ---- census: count, mean, min, max, all-equal (DErand.py:268-272) ----
     int n = 0;
-    double first = 0.0, sum = 0.0, lo = INFINITY, hi = -INFINITY;
-    bool all_equal = true;
-    for (int i = 0; i < c.S; ++i) {
+    double sum = 0.0, lo = INFINITY, hi = -INFINITY;
+    for (int i = c.lane; i < c.S; i += c.nlanes) {
         const double x = c.sign * c.tab[(int64_t)i * c.ld];
         if (!gf_finite(x)) continue;
-        if (n == 0) first = x;
-        all_equal = all_equal && (x == first);
         sum += x;
         lo = fmin(lo, x);
         hi = fmax(hi, x);
         ++n;
     }
+    n = red.sum(n);
+    sum = red.sum(sum);
+    lo = red.min(lo);
+    hi = red.max(hi);
     out[0] = out[1] = out[2] = 0.0;
     if (n <= 50) return 1;
-    if (all_equal) { out[0] = NAN; out[1] = 0.0; out[2] = 1.0; return 2; }
+    if (lo == hi) { out[0] = NAN; out[1] = 0.0; out[2] = 1.0; return 2; }     // all finite values equal
 
     // ---- start values: _skew, gamma_gen._fitstart, fit_loc_scale, _fit_loc_scale_support ----
     const double mu = sum / n;
     double m2 = 0.0, m3 = 0.0;
-    for (int i = 0; i < c.S; ++i) {
+    for (int i = c.lane; i < c.S; i += c.nlanes) {
         const double x = c.sign * c.tab[(int64_t)i * c.ld];
         if (!gf_finite(x)) continue;
         const double d = x - mu;
         m2 += d * d;
         m3 += d * d * d;
     }
-    m2 /= n;
-    m3 /= n;
+    m2 = red.sum(m2) / n;
+    m3 = red.sum(m3) / n;
     const double sk = m3 / pow(m2, 1.5);
     const double a0 = 4.0 / (1e-8 + sk * sk);
     double scale0 = sqrt(m2 / a0);                               // Shat = sqrt(var / mu2), mu2 = a
@@ -103,7 +148,7 @@ SPADE_HD inline int gamma_fit_column(const GammaColumn &c, double out[3])
         for (int j = 0; j < 3; ++j) sim[k][j] = x0[j];
     for (int k = 0; k < 3; ++k) sim[k + 1][k] = (x0[k] != 0.0) ? 1.05 * x0[k] : 0.00025;
     int fcalls = 0;
-    for (int k = 0; k < 4; ++k) { fsim[k] = gamma_penalized_nnlf(c, n, sim[k][0], sim[k][1], sim[k][2]); ++fcalls; }
+    for (int k = 0; k < 4; ++k) { fsim[k] = gamma_penalized_nnlf(c, n, sim[k][0], sim[k][1], sim[k][2], red); ++fcalls; }
 
     auto sort_simplex = [&]() {                                  // np.argsort on 4 values: insertion sort
         for (int i = 1; i < 4; ++i) {
@@ -133,7 +178,7 @@ SPADE_HD inline int gamma_fit_column(const GammaColumn &c, double out[3])
         // a function evaluation past maxfun raises in scipy and ends the iteration without a move
         auto eval = [&](const double *p, double &f) -> bool {
             if (fcalls >= maxfun) return false;
-            f = gamma_penalized_nnlf(c, n, p[0], p[1], p[2]);
+            f = gamma_penalized_nnlf(c, n, p[0], p[1], p[2], red);
             ++fcalls;
             return true;
         };
@@ -182,7 +227,7 @@ SPADE_HD inline int gamma_fit_column(const GammaColumn &c, double out[3])
         sort_simplex();
     }
     const double a = sim[0][0], loc = sim[0][1], scale = sim[0][2];
-    const double obj = gamma_penalized_nnlf(c, n, a, loc, scale);
+    const double obj = gamma_penalized_nnlf(c, n, a, loc, scale, red);
     if (!(a > 0.0 && scale > 0.0) || !gf_finite(obj)) {          // scipy raises FitError here
         out[0] = out[1] = out[2] = NAN;
         return 3;

@@ -1130,19 +1130,43 @@ int spade_ipc_close(int device, void *dptr)
 #undef IPC_TRY
 
 namespace {
-// One gene per thread: the column walk is coalesced across the genes of a warp.
-__global__ void __launch_bounds__(128)
+// One warp per gene, kGammaGenes genes per CTA.  The CTA first copies its [S][kGammaGenes] tile
+// of the table into shared memory (32-byte runs per row: whole sectors), so that the ~300
+// likelihood evaluations of a gene read its column from shared memory, lane-strided and
+// conflict-free; tables with too many rows for that are read from global memory directly.
+constexpr int kGammaGenes = 4;
+
+__global__ void __launch_bounds__(kGammaGenes * 32)
 k_gamma_fit(const double *__restrict__ tab, int S, int64_t G, int64_t ld, double sign, double *__restrict__ A,
-            double *__restrict__ B, double *__restrict__ C, int32_t *__restrict__ status)
+            double *__restrict__ B, double *__restrict__ C, int32_t *__restrict__ status, int use_smem)
 {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    extern __shared__ double cols[];                       // [kGammaGenes][S]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g0 = (int64_t)blockIdx.x * kGammaGenes;
+    if (use_smem) {
+        for (int idx = threadIdx.x; idx < S * kGammaGenes; idx += blockDim.x) {
+            const int r = idx / kGammaGenes, j = idx % kGammaGenes;
+            cols[(size_t)j * S + r] = g0 + j < G ? tab[(int64_t)r * ld + g0 + j] : NAN;
+        }
+        __syncthreads();
+    }
+    const int64_t g = g0 + warp;
     if (g >= G) return;
-    GammaColumn col{tab + g, ld, S, sign};
+    GammaColumn col;
+    col.tab = use_smem ? cols + (size_t)warp * S : tab + g;
+    col.ld = use_smem ? 1 : ld;
+    col.S = S;
+    col.sign = sign;
+    col.lane = lane;
+    col.nlanes = 32;
     double out[3];
-    status[g] = gamma_fit_column(col, out);
-    A[g] = out[0];
-    B[g] = out[1];
-    C[g] = out[2];
+    const int st = gamma_fit_column(col, out, WarpReduce());
+    if (lane == 0) {
+        status[g] = st;
+        A[g] = out[0];
+        B[g] = out[1];
+        C[g] = out[2];
+    }
 }
 }  // namespace
 
@@ -1173,7 +1197,11 @@ int spade_gamma_fit(int device, const double *table, int table_location, int64_t
     }
     G_TRY(dout.reserve(3 * (size_t)G));
     G_TRY(dst.reserve((size_t)G));
-    k_gamma_fit<<<(unsigned)((G + 127) / 128), 128>>>(dt, (int)S, G, ld, sign, dout.p, dout.p + G, dout.p + 2 * G, dst.p);
+    const size_t tile = (size_t)kGammaGenes * (size_t)S * sizeof(double);
+    const int use_smem = tile <= 96 * 1024;
+    if (use_smem) G_TRY(cudaFuncSetAttribute(k_gamma_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    k_gamma_fit<<<(unsigned)((G + kGammaGenes - 1) / kGammaGenes), kGammaGenes * 32, use_smem ? tile : 0>>>(
+        dt, (int)S, G, ld, sign, dout.p, dout.p + G, dout.p + 2 * G, dst.p, use_smem);
     G_TRY(cudaGetLastError());
     G_TRY(cudaMemcpy(A, dout.p, G * sizeof(double), cudaMemcpyDeviceToHost));
     G_TRY(cudaMemcpy(B, dout.p + G, G * sizeof(double), cudaMemcpyDeviceToHost));

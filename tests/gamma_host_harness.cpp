@@ -9,7 +9,7 @@ extern "C" void gamma_fit_table(const double *tab, int S, long G, double sign, d
     for (long g = 0; g < G; ++g) {
         spade::GammaColumn col{tab + g, G, S, sign};
         double out[3];
-        status[g] = spade::gamma_fit_column(col, out);
+        status[g] = spade::gamma_fit_column(col, out, spade::SerialReduce());
         A[g] = out[0];
         B[g] = out[1];
         C[g] = out[2];
@@ -19,5 +19,5 @@ extern "C" void gamma_fit_table(const double *tab, int S, long G, double sign, d
 extern "C" double gamma_nnlf(const double *x, int n, double a, double loc, double scale)
 {
     spade::GammaColumn col{x, 1, n, 1.0};
-    return spade::gamma_penalized_nnlf(col, n, a, loc, scale);
+    return spade::gamma_penalized_nnlf(col, n, a, loc, scale, spade::SerialReduce());
 }
