@@ -43,7 +43,7 @@ if ROOT not in sys.path:
 G_GENES, C_CELLS, N_MEMBERS, S_DRAWS = 33000, 50000, 500, 1000
 TABLES = ("up", "down", "cpm")               # DErand keeps these three (DErand.py:219-221)
 B_OUT = 8 * len(TABLES)
-SAMPLE_GENES, SAMPLE_SETS = 4096, 8
+SAMPLE_GENES, SAMPLE_SETS = 4096, 24      # ~10 s of CPU work on 16 cores; also the parity sample
 METRIC = "gene x draw hypergeometric tests per second"
 UNIT = "tests/s"
 
