@@ -119,30 +119,9 @@ def make_draws(total_sets, C, N):
 
 
 def sample_matrix(indptr, indices, counts, G, C, n_genes):
-    """Host float64 CPM rows of a density-stratified gene sample (evenly spaced over the
-    genes ordered by their number of expressing cells), reference CPM operation order."""
-    import scipy.sparse as sp
-    import torch
-    nnz_g = (indptr[1:] - indptr[:-1])
-    order = torch.argsort(nnz_g, stable=True)
-    pick = order[torch.linspace(0, G - 1, n_genes, device=order.device).round().long()]
-    pick = torch.unique(pick)                      # sorted, unique gene ids
-    lens = nnz_g[pick]
-    starts = indptr[:-1][pick]
-    sub_ptr = torch.zeros(pick.numel() + 1, dtype=torch.int64, device=pick.device)
-    sub_ptr[1:] = torch.cumsum(lens, 0)
-    pos = torch.arange(int(sub_ptr[-1]), device=pick.device)
-    row = torch.repeat_interleave(torch.arange(pick.numel(), device=pick.device), lens)
-    src = starts[row] + (pos - sub_ptr[:-1][row])
-    colsum = torch.zeros(C, dtype=torch.int64, device=pick.device)
-    colsum.index_add_(0, indices.long(), counts.long())
-    sub_idx = indices[src].cpu().numpy()
-    sub_cnt = counts[src].cpu().numpy()
-    with np.errstate(divide="ignore"):
-        inv = 1.0 / colsum.cpu().numpy()
-    data = (sub_cnt.astype(np.float64) * 1e6) * inv[sub_idx]        # utils.py:150-155 order
-    X = sp.csr_matrix((data, sub_idx, sub_ptr.cpu().numpy()), shape=(pick.numel(), C))
-    return pick.cpu().numpy(), X
+    """Host float64 CPM rows of a density-stratified gene sample (``synth.sample_rows``)."""
+    from pyspade_b200 import synth
+    return synth.sample_rows(indptr, indices, counts, G, C, n_genes)
 
 
 def cpu_port_leg(X, sets, nproc):

@@ -42,7 +42,7 @@ extern "C" {
 #define SPADE_HOST 0
 #define SPADE_DEVICE 1
 
-#define SPADE_ABI_VERSION 2
+#define SPADE_ABI_VERSION 3
 
 typedef struct spade_engine spade_engine;
 
@@ -146,6 +146,29 @@ int spade_run(spade_engine *engine, const int32_t *members, int members_location
               int32_t *k, int out_location, void *stream);
 
 /*
+ * Verdict on the member lists of every spade_run / spade_run_raw issued so far.  With host
+ * outputs spade_run reports a member cell index out of range or a duplicated cell inside a set
+ * itself; with device outputs it returns before its kernels have run, so such an error surfaces
+ * here (the call synchronises the device) or, once the kernels have finished, at the next
+ * spade_run / spade_timing of the engine.  SPADE_ERR_ARG + spade_last_error on a bad list.
+ */
+int spade_check(spade_engine *engine);
+
+/*
+ * Accuracy contract of fc and cpm.  Member sums are carried in a per-gene fixed point
+ * (2^-shift_g, chosen so that any sum over 32 768 cells fits 47 bits): the mean of same-signed
+ * values is within 2^-22 (2.4e-7) relative of the exact mean, fold changes within 2^-21, for
+ * ANY float64 matrix.  A gene whose values span too many binary orders of magnitude for that
+ * bound ("wide": a few huge cells next to tiny ones) is summed in float64 by a side kernel
+ * instead, like the reference does (scipy sparse mean, utils.py:206-208).  Count data
+ * normalised to CPM has no wide genes.  count = number of wide genes of the staged matrix with
+ * the current background; spade_run_raw / spade_expand refuse (SPADE_ERR_STATE) when it is > 0.
+ * Rows that mix signs can cancel: there the bound is absolute, 2^-22 * min |nonzero value|.
+ * Values must be finite and below 8e270 in magnitude (else SPADE_ERR_ARG at staging).
+ */
+int spade_wide_genes(const spade_engine *engine, int64_t *count);
+
+/*
  * spade_run with an explicit row stride of the result tables (elements between the rows of
  * consecutive sets; spade_run uses G).  With out_row_stride = P*G and table pointers offset
  * by rank*G, P ranks interleave their rows (set i of rank r = row i*P + r) in ONE table:
@@ -180,6 +203,42 @@ int spade_run_raw(spade_engine *engine, const int32_t *members, int members_loca
 int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_t raw_row_stride,
                  const int64_t *set_sizes, double *up, double *down, double *fc, double *cpm,
                  int32_t *k, int64_t out_row_stride, void *stream);
+
+/*
+ * Raw form routed by GENE BLOCK - the exchange step of the multi-GPU path (one process per
+ * GPU, sets sharded over the GPUs, matrix replicated).  The genes are cut into `nblocks`
+ * consecutive blocks (boundaries on multiples of genes_per_part, spade_dims), block b owned by
+ * GPU b; a GPU that has tested its share of the sets stores the word of (set i, gene g) straight
+ * into the owner's table, blocks[b].base[(first_row + i * row_step) * blocks[b].ld + (g -
+ * gene_begin)] - its own memory for its own block, a peer's (spade_ipc_open) over NVLink /
+ * NVSwitch for the others, from inside the test kernel while it computes.  After all GPUs have
+ * finished (any barrier ordered after the launch stream), every GPU holds ALL sets x ITS genes
+ * and finishes them with spade_expand_block: the all-to-all is fused into the kernel, every GPU
+ * receives only (P-1)/P of 1/P of the words, and the layout - all draws of a gene on one GPU -
+ * is what the per-gene consumers of the tables need next (gamma fit over the draws
+ * DErand.py:250-292, empirical p-values global.py:177-187, the column-compressed MAT tables).
+ * first_row / row_step place this GPU's sets in the global set order (DErand: draw i of rank r
+ * is row i * P + r; DEobs: a contiguous run of rows per rank).
+ * spade_expand_block: rows x gene_count words (column j = gene gene_begin + j) into tables with
+ * the same column meaning; set_sizes[rows] on the host.  spade_expand = the block [0, G).
+ */
+typedef struct spade_gene_block {
+    uint64_t *base;      /* device pointer of the owner's word table (own or peer memory) */
+    int64_t ld;          /* elements between its rows, >= gene_end - gene_begin */
+    int64_t gene_begin;  /* first gene of the block, multiple of genes_per_part */
+    int64_t gene_end;    /* one past its last gene */
+} spade_gene_block;
+int spade_run_raw_blocks(spade_engine *engine, const int32_t *members, int members_location,
+                         const int64_t *offsets, int64_t S, const spade_gene_block *blocks, int nblocks,
+                         int64_t first_row, int64_t row_step, void *stream);
+int spade_expand_block(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_t raw_row_stride,
+                       int64_t gene_begin, int64_t gene_count, const int64_t *set_sizes, double *up,
+                       double *down, double *fc, double *cpm, int32_t *k, int64_t out_row_stride, void *stream);
+
+/* Strided copy between device and host memory on a stream (cudaMemcpy2DAsync): a gene block
+ * [rows][width] of a device table into / out of a wider host table. */
+int spade_memcpy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width_bytes,
+                   int64_t rows, int device_to_host, void *stream);
 
 /*
  * Plain device memory that can be shared between the processes of one node (one process per
@@ -226,6 +285,28 @@ int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_
  */
 int spade_gamma_fit(int device, const double *table, int table_location, int64_t S, int64_t G,
                     int64_t ld, double sign, double *A, double *B, double *C, int32_t *status);
+
+/*
+ * Significance scoring of observed regions against the DErand background - the arithmetic of
+ * `pySpade global` / `pySpade local` that consumes the tables of this path
+ * (pySpade/global.py:107-187, local.py:104-177), for all genes of R regions at once:
+ *   p            = obs[r][g] with 0 -> 1, +-inf -> 0, nan -> 0          (global.py:118-123)
+ *   score[r][g]  = scipy.stats.gamma.logsf(-p, A[g], B[g], C[g])        (global.py:151-171;
+ *                  "Significance_score"; nan where the parameters are invalid, e.g. the
+ *                  (0, 0, 0) of a gene DErand skipped or the (nan, 0, 1) of a constant gene)
+ *   emp[r][g]    = #{draws s : rand[s][g] < p} / S                       (global.py:181,187;
+ *                  "pval-empirical"; nan entries of rand never count, -inf entries always do)
+ * rand: the DErand table [S][rand_ld] (up or down log p, as saved), obs: the DEobs rows
+ * [R][obs_ld] of the same direction, host or device per *_location; A, B, C: host float64[G]
+ * (the Up_/Down_dist_gamma npy vectors).  score / emp: [R][out_ld], host or device per
+ * out_location; either may be NULL (then its inputs may be NULL too).  Synchronous.
+ * gamma.logsf = log(gammaincc(a, (x - loc) / scale)) with rv_continuous.logsf's support and
+ * argument rules; agrees with scipy within 1e-6 relative (+ 1e-15 absolute next to 0, where
+ * scipy's own double-rounded sf decides), see tests/test_score_gpu.py.  S <= 16384 draws.
+ */
+int spade_score(int device, const double *rand, int rand_location, int64_t S, int64_t G, int64_t rand_ld,
+                const double *obs, int obs_location, int64_t R, int64_t obs_ld, const double *A, const double *B,
+                const double *C, double *score, double *emp, int out_location, int64_t out_ld);
 
 /* Page-locked host memory for result tables (fast device->host copies). */
 int spade_host_alloc(void **ptr, int64_t bytes);

@@ -11,13 +11,19 @@ LIB_PATH = os.environ.get("SPADE_LIB") or os.path.join(_PKG, "libspade_b200.so")
 
 SPADE_OK, SPADE_ERR_ARG, SPADE_ERR_CUDA, SPADE_ERR_STATE = 0, 1, 2, 3
 SPADE_HOST, SPADE_DEVICE = 0, 1
-SPADE_ABI_VERSION = 2
+SPADE_ABI_VERSION = 3
 SPADE_OPT_TAIL_TABLE, SPADE_OPT_MEMBER_BLOCK, SPADE_OPT_GENES_PER_PART, SPADE_OPT_SORT_MEMBERS = 1, 2, 3, 4
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_f64p = ctypes.POINTER(ctypes.c_double)
 c_vpp = ctypes.POINTER(ctypes.c_void_p)
+
+
+class GeneBlock(ctypes.Structure):
+    """``spade_gene_block`` of ``include/spade.h``."""
+    _fields_ = [("base", ctypes.c_void_p), ("ld", ctypes.c_int64), ("gene_begin", ctypes.c_int64),
+                ("gene_end", ctypes.c_int64)]
 
 # name -> (restype, argtypes); every symbol include/spade.h declares
 SIGNATURES = {
@@ -46,11 +52,22 @@ SIGNATURES = {
     "spade_expand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "spade_run_raw_blocks": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                            ctypes.c_int64, ctypes.c_void_p]),
+    "spade_expand_block": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int64, ctypes.c_void_p]),
+    "spade_memcpy2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
     "spade_device_alloc": (ctypes.c_int, [ctypes.c_int, c_vpp, ctypes.c_int64]),
     "spade_device_free": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "spade_ipc_export": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p]),
     "spade_ipc_open": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, c_vpp]),
     "spade_ipc_close": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
+    "spade_check": (ctypes.c_int, [ctypes.c_void_p]),
+    "spade_wide_genes": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
     "spade_timing": (ctypes.c_int, [ctypes.c_void_p, c_f64p, c_f64p, c_i64p, ctypes.c_int]),
     "spade_hypergeom": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
@@ -58,6 +75,10 @@ SIGNATURES = {
     "spade_gamma_fit": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                        ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p]),
+    "spade_score": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                   ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]),
     "spade_host_alloc": (ctypes.c_int, [c_vpp, ctypes.c_int64]),
     "spade_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "spade_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),

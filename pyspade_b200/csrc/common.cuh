@@ -22,6 +22,9 @@ constexpr int kMaxGenesPerPart = 1 << kSlotBits;      // 8192
 // A warp accumulates at most this many member cells before its accumulators are drained:
 // the 16-bit count field and the 47-bit sum budget (see stage.cuh) are sized for it.
 constexpr int kMemberBlock = 32768;
+// Guaranteed relative accuracy of a fixed-point member mean of same-signed values; genes that
+// cannot meet it take the float64 side path (stage.cuh, wide.cuh).  Fold changes: twice this.
+constexpr double kWideRelBound = 0x1p-22;             // 2.4e-7
 constexpr int kSegAlign = 16;                         // entries: segments start on 128-byte lines
 #ifndef SPADE_DENSE_REGS
 #define SPADE_DENSE_REGS 1
@@ -33,7 +36,8 @@ struct __align__(16) GeneMeta {      // one per gene, fixed by the matrix and th
     int32_t n;                       // #{cells : x <= cutoff}             (utils.py:200,211)
     int16_t shift;                   // fixed point: fx = round(value * 2^shift)
     uint8_t negmode;                 // cutoff < 0: flag marks the LOW side, k = count
-    uint8_t pad;
+    uint8_t wide;                    // dynamic range too wide for the fixed point: the member
+                                     // means of this gene come from the float64 side path (wide.cuh)
     union {
         long long rowsum;            // complement background: sum of fx over all cells
         double bgmean;               // NC background: mean over the NC cells (utils.py:258)
@@ -45,6 +49,14 @@ struct __align__(16) TabMeta {       // one per gene, per run: window of the tai
     int32_t lo;                      // k of that entry
     int32_t len;                     // entries; 0 = no table for this gene
 };
+
+// Device-side error word: lives in page-locked host memory mapped into the device, so the host
+// can read it at any time without synchronising (1 bad matrix index, 2 member out of range,
+// 3 non-finite matrix value, 4 duplicate member).  A plain store: any code is as good as another.
+__device__ __forceinline__ void flag_error(int *err, int code)
+{
+    *(volatile int *)err = code;
+}
 
 __device__ __forceinline__ double pow2_double(int e)   // 2^e for -1022 <= e <= 1023
 {
@@ -94,6 +106,25 @@ __device__ inline double block_max(double v, double *scratch)
     if (warp == 0) {
         double t = lane < nwarp ? scratch[lane] : 0.0;
         t = warp_max(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// Minimum over the block (identity +inf); result valid in every thread.
+__device__ inline double block_min(double v, double *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < nwarp ? scratch[lane] : INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = fmin(t, __shfl_xor_sync(0xffffffffu, t, o));
         if (lane == 0) scratch[32] = t;
     }
     __syncthreads();

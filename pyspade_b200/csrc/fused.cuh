@@ -17,6 +17,9 @@ namespace spade {
 #ifndef SPADE_ITERS
 #define SPADE_ITERS 3
 #endif
+#ifndef SPADE_FIN_BATCH
+#define SPADE_FIN_BATCH 2
+#endif
 #ifndef SPADE_MIN_CTAS
 #define SPADE_MIN_CTAS 6
 #endif
@@ -28,6 +31,7 @@ __device__ __forceinline__ unsigned long long stream_load(const unsigned long lo
 }
 
 constexpr int kWarpsPerCta = 4;
+constexpr int kFinBatch = SPADE_FIN_BATCH;           // genes per lane whose finalize loads are in flight together
 constexpr int kMemberBatch = SPADE_MEMBER_BATCH;   // member cells whose segments are in flight per warp
 constexpr int kIters = SPADE_ITERS;                // unrolled 32-entry steps per member segment
 static_assert(32 % kMemberBatch == 0, "a batch must not straddle two 32-member groups");
@@ -46,46 +50,90 @@ struct FinCtx {
     int64_t ld;                   // row stride (elements)
 };
 
-// One (gene, set) test from its member sum / member count (utils.py:203-215, 257-266).
-__device__ __forceinline__ void finalize_test(const FinCtx &f, int64_t row, int64_t g, long long sumfx,
-                                              int cnt, long long N, double invN, double invRest)
+// One (gene, set) test from its member sum / member count (utils.py:203-215, 257-266), in two
+// steps so that a lane can have the metadata and tail-table loads of several genes in flight:
+// fin_load issues the loads (gene metadata, table window, the table entry when k is inside the
+// window), fin_store does the arithmetic and the stores.
+// The float arithmetic of a finished test, with explicit roundings (no FMA contraction): the
+// same test gives the same bits from every kernel that finishes it (fused, split, expand).
+__device__ __forceinline__ double fixed_mean(long long sumfx, int shift, double inv_count)
 {
-    const GeneMeta mt = f.meta[g];
-    const int kk = mt.negmode ? cnt : (int)(N - cnt);
-    const double inv = pow2_double(-mt.shift);
-    const double mean_set = ((double)sumfx * inv) * invN;
+    return __dmul_rn(__dmul_rn((double)sumfx, pow2_double(-shift)), inv_count);
+}
+
+__device__ __forceinline__ double fold_change(double mean_set, double mean_bg)    // utils.py:207 / :258
+{
+    return __ddiv_rn(__dadd_rn(mean_set, 0.01), __dadd_rn(mean_bg, 0.01));
+}
+
+struct FinItem {
+    GeneMeta mt;
+    double2 tv;
+    long long sumfx;
+    int kk;
+    int how;          // 0 nan, 1 upper support edge, 2 table entry in tv, 3 evaluate directly
+};
+
+__device__ __forceinline__ void fin_load(const FinCtx &f, int64_t g, long long sumfx, int cnt, long long N,
+                                         FinItem &it)
+{
+    it.mt = f.meta[g];
+    it.sumfx = sumfx;
+    it.kk = it.mt.negmode ? cnt : (int)(N - cnt);
+    it.how = 3;
+    if (!(f.up || f.down)) return;
+    if (it.kk == 0 || f.M == 0 || it.mt.n == 0 || N == 0) {     // all([k, M, n, N]), utils.py:212-213
+        it.how = 0;
+    } else if (it.kk >= min(it.mt.n, (int)N)) {                 // upper support edge: no lookup needed
+        it.how = 1;                                              // (what hyper_tails returns first)
+    } else if (f.tmeta) {
+        const TabMeta tm = f.tmeta[g];
+        const unsigned d = (unsigned)(it.kk - tm.lo);
+        if (d < (unsigned)tm.len) {
+            it.tv = f.tab[tm.off + d];
+            it.how = 2;
+        }
+    }
+}
+
+__device__ __forceinline__ void fin_store(const FinCtx &f, int64_t row, int64_t g, const FinItem &it, long long N,
+                                          double invN, double invRest)
+{
+    const double mean_set = fixed_mean(it.sumfx, it.mt.shift, invN);
     const int64_t o = row * f.ld + g;
     if (f.cpm) f.cpm[o] = mean_set;
     if (f.fc) {
-        const double mean_bg = f.nc_mode ? mt.bgmean : ((double)(mt.rowsum - sumfx) * inv) * invRest;
-        f.fc[o] = (mean_set + 0.01) / (mean_bg + 0.01);
+        const double mean_bg = f.nc_mode ? it.mt.bgmean : fixed_mean(it.mt.rowsum - it.sumfx, it.mt.shift, invRest);
+        f.fc[o] = fold_change(mean_set, mean_bg);
     }
-    if (f.k) f.k[o] = kk;
+    if (f.k) f.k[o] = it.kk;
     if (f.up || f.down) {
         double lc, ls;
-        if (kk == 0 || f.M == 0 || mt.n == 0 || N == 0) {       // all([k, M, n, N]), utils.py:212-213
+        if (it.how == 0) {
             lc = ls = __longlong_as_double(0x7ff8000000000000ll);
-        } else if (kk >= min(mt.n, (int)N)) {                   // upper support edge: no lookup needed
-            lc = 0.0;                                            // (what hyper_tails returns first)
+        } else if (it.how == 1) {
+            lc = 0.0;
             ls = -INFINITY;
+        } else if (it.how == 2) {
+            lc = it.tv.x;
+            ls = it.tv.y;
         } else {
-            bool hit = false;
-            if (f.tmeta) {
-                const TabMeta tm = f.tmeta[g];
-                const unsigned d = (unsigned)(kk - tm.lo);
-                if (d < (unsigned)tm.len) {
-                    const double2 v = f.tab[tm.off + d];
-                    lc = v.x;
-                    ls = v.y;
-                    hit = true;
-                }
-            }
-            if (!hit) hyper_tails(kk, f.M, mt.n, (int)N, f.lf, lc, ls);
+            hyper_tails(it.kk, f.M, it.mt.n, (int)N, f.lf, lc, ls);
         }
         if (f.up) f.up[o] = lc;
         if (f.down) f.down[o] = ls;
     }
 }
+
+__device__ __forceinline__ void finalize_test(const FinCtx &f, int64_t row, int64_t g, long long sumfx,
+                                              int cnt, long long N, double invN, double invRest)
+{
+    FinItem it;
+    fin_load(f, g, sumfx, cnt, N, it);
+    fin_store(f, row, g, it, N, invN, invRest);
+}
+
+constexpr int kMaxGeneBlocks = 16;   // destinations of the routed raw form (GPUs of one node)
 
 struct RunArgs {
     const unsigned long long *ent;
@@ -105,6 +153,14 @@ struct RunArgs {
     int *gcnt;
     unsigned long long *raw;      // non-null: store the accumulator words instead of finished tests
     int64_t raw_ld;
+    // raw form routed by gene block (multi-GPU exchange): partitions [dst_pbegin[b], dst_pbegin[b+1])
+    // go to table dst_base[b] (row stride dst_ld[b], column 0 = first gene of the block), set u of
+    // the launch to row raw_row0 + u * raw_row_step.  ndst == 0: the single table `raw`.
+    int ndst;
+    unsigned long long *dst_base[kMaxGeneBlocks];
+    int64_t dst_ld[kMaxGeneBlocks];
+    int dst_pbegin[kMaxGeneBlocks + 1];
+    int64_t raw_row0, raw_row_step;
     int p0, p1;                   // gene partitions of this launch
     int Gp;
     int64_t C;
@@ -180,7 +236,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
                 b = se.x;
                 e = se.y;
             } else {
-                atomicExch(a.err, 2);
+                flag_error(a.err, 2);
             }
         }
     };
@@ -265,18 +321,39 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         __syncwarp();
     }
 
-    if (!kSplit && a.raw) {
+    if (!kSplit && a.ndst > 0) {
+        // raw form, routed: this partition's words go to the owner of its gene block (a table in
+        // this GPU's or a peer GPU's memory; coalesced 256-byte stores over NVLink)
+        int b = 0;
+        while (b + 1 < a.ndst && p >= a.dst_pbegin[b + 1]) ++b;
+        unsigned long long *dst = a.dst_base[b] + (a.raw_row0 + row * a.raw_row_step) * a.dst_ld[b] +
+                                  (g0 - (int64_t)a.dst_pbegin[b] * a.Gp);
+        for (int j = lane; j < ng; j += 32) dst[j] = acc[j];
+    } else if (!kSplit && a.raw) {
         // raw form: the accumulator words leave as they are (8 bytes per test instead of 24-36);
         // whoever receives them finishes the tests with k_expand
         for (int j = lane; j < ng; j += 32) a.raw[row * a.raw_ld + g0 + j] = acc[j];
     } else if (!kSplit) {
         const double invN = 1.0 / (double)N;
         const double invRest = 1.0 / (double)((long long)a.C - N);
-        for (int j = lane; j < ng; j += 32) {
-            const long long v = (long long)acc[j];
-            const long long sumfx = (v << 16) >> 16;
-            const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
-            finalize_test(a.fin, row, g0 + j, sumfx, cnt, N, invN, invRest);
+        // kFinBatch genes per lane at a time: their metadata / table loads overlap
+        for (int j0 = lane; j0 < ng; j0 += 32 * kFinBatch) {
+            FinItem it[kFinBatch];
+#pragma unroll
+            for (int u = 0; u < kFinBatch; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < ng) {
+                    const long long v = (long long)acc[j];
+                    const long long sumfx = (v << 16) >> 16;
+                    const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
+                    fin_load(a.fin, g0 + j, sumfx, cnt, N, it[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kFinBatch; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < ng) fin_store(a.fin, row, g0 + j, it[u], N, invN, invRest);
+            }
         }
     } else {
         for (int j = lane; j < ng; j += 32) {
@@ -350,7 +427,7 @@ __global__ void k_check_duplicates(const int32_t *__restrict__ sorted, const int
             const int64_t mid = (lo + hi) >> 1;
             if (offsets[mid] > i) hi = mid; else lo = mid + 1;
         }
-        if (lo > S || offsets[lo] != i + 1) atomicExch(err, 4);
+        if (lo > S || offsets[lo] != i + 1) flag_error(err, 4);
     }
 }
 
@@ -360,23 +437,24 @@ __global__ void k_check_duplicates(const int32_t *__restrict__ sorted, const int
 // coalesced across the genes of a warp.
 constexpr int kExpandRows = 16;
 
+// Gene block [g_begin, g_begin + g_count): column j of raw and of the tables = gene g_begin + j.
 __global__ void __launch_bounds__(256)
 k_expand(const FinCtx f, const unsigned long long *__restrict__ raw, int64_t raw_ld,
-         const int64_t *__restrict__ sizes, int64_t rows)
+         const int64_t *__restrict__ sizes, int64_t rows, int64_t g_begin, int64_t g_count)
 {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= f.G) return;
+    const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (col >= g_count) return;
+    const int64_t g = g_begin + col;
     const int64_t r0 = (int64_t)blockIdx.y * kExpandRows;
     const int64_t r1 = min(rows, r0 + kExpandRows);
     const GeneMeta mt = f.meta[g];
-    const double inv = pow2_double(-mt.shift);
     TabMeta tm;
     tm.off = 0; tm.lo = 0; tm.len = 0;
     if (f.tmeta) tm = f.tmeta[g];
     unsigned long long w[kExpandRows];
 #pragma unroll
     for (int i = 0; i < kExpandRows; ++i)
-        w[i] = r0 + i < r1 ? __ldcs(raw + (r0 + i) * raw_ld + g) : 0ull;
+        w[i] = r0 + i < r1 ? __ldcs(raw + (r0 + i) * raw_ld + col) : 0ull;
 #pragma unroll
     for (int i = 0; i < kExpandRows; ++i) {
         const int64_t row = r0 + i;
@@ -386,13 +464,13 @@ k_expand(const FinCtx f, const unsigned long long *__restrict__ raw, int64_t raw
         const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
         const long long N = sizes[row];
         const int kk = mt.negmode ? cnt : (int)(N - cnt);
-        const double mean_set = ((double)sumfx * inv) * (1.0 / (double)N);
-        const int64_t o = row * f.ld + g;
+        const double mean_set = fixed_mean(sumfx, mt.shift, 1.0 / (double)N);
+        const int64_t o = row * f.ld + col;
         if (f.cpm) __stcs(f.cpm + o, mean_set);
         if (f.fc) {
             const double mean_bg = f.nc_mode ? mt.bgmean
-                                             : ((double)(mt.rowsum - sumfx) * inv) * (1.0 / (double)((long long)f.M - N));
-            __stcs(f.fc + o, (mean_set + 0.01) / (mean_bg + 0.01));
+                                             : fixed_mean(mt.rowsum - sumfx, mt.shift, 1.0 / (double)((long long)f.M - N));
+            __stcs(f.fc + o, fold_change(mean_set, mean_bg));
         }
         if (f.k) f.k[o] = kk;
         if (f.up || f.down) {

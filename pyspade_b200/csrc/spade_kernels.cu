@@ -34,8 +34,10 @@
 #include "common.cuh"
 #include "fused.cuh"
 #include "gamma_fit.cuh"
+#include "score.cuh"
 #include "stage.cuh"
 #include "tails.cuh"
+#include "wide.cuh"
 
 using namespace spade;
 
@@ -49,6 +51,7 @@ constexpr int64_t kMaxTableEntries = int64_t(1) << 26;      // tail table: 1 GiB
 constexpr int kDefaultGenesPerPart = 1024;
 constexpr int kTargetCopyGroups = 12;                       // host outputs: strips per batch
 constexpr double kDenseMinEntries = 6.0;                    // dense block must remove >= this many entries per cell
+constexpr int64_t kMaxBitmaskBytes = int64_t(1) << 30;      // wide-gene side path: membership bitmasks per chunk of sets
 
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
@@ -95,8 +98,13 @@ struct spade_engine {
     DevBuf<int32_t> n;
     DevBuf<GeneMeta> meta;
     DevBuf<uint8_t> ncmask;
-    DevBuf<int> err;
+    int *h_err = nullptr, *d_err = nullptr;   // error word: mapped page-locked host memory (common.cuh flag_error)
     std::vector<int32_t> h_n;
+    // wide genes (float64 side path, wide.cuh): ascending gene ids, host and device copies
+    DevBuf<uint8_t> wide_flag;
+    DevBuf<int32_t> wide_genes;
+    std::vector<int32_t> h_wide;
+    DevBuf<uint32_t> bits_buf[2];
 
     // run workspace
     DevBuf<int32_t> members, members_sorted;
@@ -170,12 +178,22 @@ struct spade_engine {
         return SPADE_OK;
     }
 
+    int ensure_error_word()
+    {
+        if (h_err) return SPADE_OK;
+        CUDA_TRY(cudaHostAlloc((void **)&h_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        *h_err = 0;
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&d_err, h_err, 0));
+        return SPADE_OK;
+    }
+
+    // What the kernels that have FINISHED so far flagged; never waits for the device.  Callers
+    // that need the verdict on everything they launched synchronise first.
     int check_device_error(const char *what)
     {
-        int h = 0;
-        CUDA_TRY(cudaMemcpy(&h, err.p, sizeof(int), cudaMemcpyDeviceToHost));
+        const int h = h_err ? *(volatile int *)h_err : 0;
         if (h != 0) {
-            CUDA_TRY(cudaMemset(err.p, 0, sizeof(int)));
+            *(volatile int *)h_err = 0;
             const char *m = h == 2   ? ": member cell index out of range"
                             : h == 3 ? ": matrix holds non-finite (or > 8e270) values"
                             : h == 4 ? ": duplicate cell index inside a cell set"
@@ -212,7 +230,8 @@ struct spade_engine {
         a.median = median.p;
         a.n = n.p;
         a.meta = meta.p;
-        a.err = err.p;
+        a.err = d_err;
+        a.wide_flag = wide_flag.p;
         if (G > 0) k_gene_stage<<<(unsigned)G, kStageThreads, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         if (nnz > 0 && bank_order) {
@@ -222,17 +241,27 @@ struct spade_engine {
             CUDA_TRY(cudaGetLastError());
         }
         h_n.resize((size_t)G);
-        if (G > 0)
+        std::vector<uint8_t> hw((size_t)G);
+        if (G > 0) {
             CUDA_TRY(cudaMemcpyAsync(h_n.data(), n.p, G * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(hw.data(), wide_flag.p, G * sizeof(uint8_t), cudaMemcpyDeviceToHost, st));
+        }
         CUDA_TRY(cudaStreamSynchronize(st));
+        h_wide.clear();
+        for (int64_t g = 0; g < G; ++g)
+            if (hw[g]) h_wide.push_back((int32_t)g);
+        if (!h_wide.empty()) {
+            CUDA_TRY(wide_genes.reserve(h_wide.size()));
+            CUDA_TRY(cudaMemcpy(wide_genes.p, h_wide.data(), h_wide.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
         return check_device_error("staging");
     }
 
     // Everything after the CSR (indptr/indices/values) is resident on the device.
     int build(cudaStream_t st)
     {
-        CUDA_TRY(err.reserve(1));
-        CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+        int erc = ensure_error_word();
+        if (erc != SPADE_OK) return erc;
 
         Gp = gp_request > 0 ? gp_request : kDefaultGenesPerPart;
         Gp = std::min<int64_t>(Gp, std::max<int64_t>(32, (G + 31) / 32 * 32));
@@ -250,6 +279,7 @@ struct spade_engine {
         CUDA_TRY(median.reserve(G));
         CUDA_TRY(n.reserve(G));
         CUDA_TRY(meta.reserve(G));
+        CUDA_TRY(wide_flag.reserve(G));
         CUDA_TRY(ncmask.reserve(C));
         CUDA_TRY(dslot.reserve(G));
         CUDA_TRY(dgene.reserve((size_t)P * kDenseLanes));
@@ -309,7 +339,7 @@ struct spade_engine {
             CUDA_TRY(count.reserve(np));
             CUDA_TRY(cudaMemsetAsync(count.p, 0, np * sizeof(uint32_t), st));
             if (G > 0 && nnz > 0) {
-                k_part_hist<<<(unsigned)G, kStageThreads, 0, st>>>(indptr.p, indices.p, C, Gp, dslot.p, count.p, err.p);
+                k_part_hist<<<(unsigned)G, kStageThreads, 0, st>>>(indptr.p, indices.p, C, Gp, dslot.p, count.p, d_err);
                 CUDA_TRY(cudaGetLastError());
             }
             k_pad_counts<<<grid_for(np, 256), 256, 0, st>>>(count.p, (int64_t)np, C, dense_on.p, cursor.p);
@@ -441,12 +471,63 @@ struct spade_engine {
         return SPADE_OK;
     }
 
+    // Float64 means of the wide genes in [g0, g1) for sets [s0, s0 + Sb) of the uploaded batch,
+    // written over what the fixed-point path left in fc / cpm (row 0 = set s0, row stride ld).
+    // Ordered on `st` after the kernels that wrote those tables.  `which`: bitmask buffer to use
+    // (two streams may run this at the same time in the host-output pipeline).
+    int fix_wide(cudaStream_t st, int which, const int32_t *d_members, int64_t s0, int64_t Sb, int64_t g0,
+                 int64_t g1, double *fc, double *cpm, int64_t ld)
+    {
+        if (h_wide.empty() || (!fc && !cpm) || Sb <= 0) return SPADE_OK;
+        const size_t lo = std::lower_bound(h_wide.begin(), h_wide.end(), (int32_t)g0) - h_wide.begin();
+        const size_t hi = std::lower_bound(h_wide.begin(), h_wide.end(), (int32_t)std::min<int64_t>(g1, 0x7fffffff)) - h_wide.begin();
+        if (hi <= lo) return SPADE_OK;
+        const int64_t words = (C + 31) / 32;
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(Sb, kMaxBitmaskBytes / (words * 4)));
+        DevBuf<uint32_t> &bits = bits_buf[which];
+        CUDA_TRY(bits.reserve((size_t)(chunk * words)));
+        for (int64_t c0 = 0; c0 < Sb; c0 += chunk) {
+            const int64_t nc = std::min(chunk, Sb - c0);
+            CUDA_TRY(cudaMemsetAsync(bits.p, 0, (size_t)(nc * words) * sizeof(uint32_t), st));
+            for (int64_t b0 = 0; b0 < nc; b0 += 0x7fffffff) {
+                const int64_t nb = std::min<int64_t>(nc - b0, 0x7fffffff);
+                k_set_bitmask<<<(unsigned)nb, 256, 0, st>>>(d_members, offsets.p, s0 + c0 + b0, nb, C, words,
+                                                           bits.p + b0 * words);
+                CUDA_TRY(cudaGetLastError());
+            }
+            WideArgs w;
+            w.indptr = indptr.p; w.indices = indices.p; w.values = values.p; w.meta = meta.p;
+            w.bits = bits.p; w.words = words; w.offsets = offsets.p; w.C = C; w.nc_mode = n_nc > 0;
+            w.ld = ld;
+            for (int64_t r0 = 0; r0 < nc; r0 += (int64_t)65535 * kWideWarps) {           // gridDim.y limit
+                const int64_t nr = std::min<int64_t>(nc - r0, (int64_t)65535 * kWideWarps);
+                w.bits = bits.p + r0 * words;
+                w.s0 = s0 + c0 + r0;
+                w.S = nr;
+                w.fc = fc ? fc + (c0 + r0) * ld : nullptr;
+                w.cpm = cpm ? cpm + (c0 + r0) * ld : nullptr;
+                for (size_t i0 = lo; i0 < hi; i0 += 0x7fffffff) {
+                    w.genes = wide_genes.p + i0;
+                    w.nw = (int)std::min<size_t>(hi - i0, 0x7fffffff);
+                    const dim3 grid((unsigned)w.nw, (unsigned)((nr + kWideWarps - 1) / kWideWarps));
+                    k_wide_means<<<grid, kWideWarps * 32, 0, st>>>(w);
+                    CUDA_TRY(cudaGetLastError());
+                }
+            }
+            launches += 2;
+        }
+        return SPADE_OK;
+    }
+
     void free_all()
     {
         indptr.release(); indices.release(); values.release(); pptr.release(); cursor.release();
         seg.release(); dslot.release(); dgene.release(); dense_on.release();
         ent.release(); median.release(); lf.release(); n.release(); meta.release(); ncmask.release();
-        err.release(); members.release(); members_sorted.release(); sort_temp.release();
+        wide_flag.release(); wide_genes.release(); bits_buf[0].release(); bits_buf[1].release();
+        if (h_err) cudaFreeHost(h_err);
+        h_err = d_err = nullptr;
+        members.release(); members_sorted.release(); sort_temp.release();
         offsets.release();
         for (int i = 0; i < 2; ++i) { tmeta_buf[i].release(); tab_buf[i].release(); }
         blk_row.release(); blk_cnt.release(); blk_off.release(); gsum.release(); gcnt.release();
@@ -530,8 +611,7 @@ int create_common(int device, int64_t G, int64_t C, const int64_t *indptr, const
     e->nnz = nnz;
     E_TRY(e->indices.reserve(nnz));
     E_TRY(e->values.reserve(nnz));
-    E_TRY(e->err.reserve(1));
-    E_TRY(cudaMemset(e->err.p, 0, sizeof(int)));
+    if (e->ensure_error_word() != SPADE_OK) return bail(SPADE_ERR_CUDA);
     if (nnz > 0) {
         E_TRY(cudaMemcpy(e->indices.p, indices, nnz * sizeof(int32_t), kind));
         if (counts) {
@@ -541,7 +621,7 @@ int create_common(int device, int64_t G, int64_t C, const int64_t *indptr, const
             E_TRY(colsum.reserve(C));
             E_TRY(cudaMemcpy(dcounts.p, counts, nnz * sizeof(int32_t), kind));
             E_TRY(cudaMemsetAsync(colsum.p, 0, C * sizeof(unsigned long long), st));
-            k_col_sums<<<grid_for(nnz, 256), 256, 0, st>>>(e->indices.p, dcounts.p, nnz, C, colsum.p, e->err.p);
+            k_col_sums<<<grid_for(nnz, 256), 256, 0, st>>>(e->indices.p, dcounts.p, nnz, C, colsum.p, e->d_err);
             E_TRY(cudaGetLastError());
             k_cpm<<<grid_for(nnz, 256), 256, 0, st>>>(e->indices.p, dcounts.p, nnz, C, colsum.p, e->values.p);
             E_TRY(cudaGetLastError());
@@ -675,7 +755,8 @@ int spade_cpm_values(spade_engine *engine, double *values)
 static int run_impl(spade_engine *engine, const int32_t *members, int members_location,
                     const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
                     int32_t *k, int out_location, int64_t out_row_stride, void *stream,
-                    unsigned long long *raw = nullptr)
+                    unsigned long long *raw = nullptr, const spade_gene_block *blocks = nullptr, int nblocks = 0,
+                    int64_t first_row = 0, int64_t row_step = 1)
 {
     if (!engine) return SPADE_ERR_ARG;
     CUDA_TRY(cudaSetDevice(engine->device));
@@ -691,6 +772,15 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
     const int64_t total = offsets[S];
     if (total > 0 && !members) { set_error("members is NULL"); return SPADE_ERR_ARG; }
     if (S == 0 || engine->G == 0) return SPADE_OK;
+    {   // member errors of earlier device-output runs that have finished by now (see spade_check)
+        int rc = engine->check_device_error("an earlier spade_run");
+        if (rc != SPADE_OK) return rc;
+    }
+    if (raw && !engine->h_wide.empty()) {
+        set_error("the raw form is not available: the matrix holds genes that need the float64 side path "
+                  "(spade_wide_genes)");
+        return SPADE_ERR_STATE;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t G = engine->G, C = engine->C;
     const int P = engine->P;
@@ -731,7 +821,7 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
                                                         total, S, engine->offsets.p, engine->offsets.p + 1, st));
         }
         d_members = engine->members_sorted.p;
-        k_check_duplicates<<<grid_for(total, 256), 256, 0, st>>>(d_members, engine->offsets.p, S, total, engine->err.p);
+        k_check_duplicates<<<grid_for(total, 256), 256, 0, st>>>(d_members, engine->offsets.p, S, total, engine->d_err);
         CUDA_TRY(cudaGetLastError());
         engine->launches += 2;
     }
@@ -770,8 +860,12 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
 
         bool table = false;
         if (!raw && uniform && N0 > 0 && (engine->tail_mode == 2 || (engine->tail_mode == 1 && Sb >= 32))) {
-            int rc = engine->build_tail_table(N0, st, &table);
-            if (rc != SPADE_OK) return rc;
+            if (engine->tab_N == N0 && engine->tab_epoch == engine->bg_epoch) {
+                table = true;      // a pure function of (matrix, background, N): kept across calls
+            } else {
+                int rc = engine->build_tail_table(N0, st, &table);
+                if (rc != SPADE_OK) return rc;
+            }
         }
 
         RunArgs a;
@@ -786,9 +880,20 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
         a.S = Sb;
         a.Gp = engine->Gp;
         a.C = C;
-        a.err = engine->err.p;
-        a.raw = raw ? raw + s0 * out_row_stride : nullptr;
+        a.err = engine->d_err;
+        a.raw = (raw && !blocks) ? raw + s0 * out_row_stride : nullptr;
         a.raw_ld = out_row_stride;
+        if (blocks) {
+            a.ndst = nblocks;
+            for (int b = 0; b < nblocks; ++b) {
+                a.dst_base[b] = (unsigned long long *)blocks[b].base;
+                a.dst_ld[b] = blocks[b].ld;
+                a.dst_pbegin[b] = (int)(blocks[b].gene_begin / engine->Gp);
+            }
+            a.dst_pbegin[nblocks] = P;
+            a.raw_row0 = first_row + s0 * row_step;
+            a.raw_row_step = row_step;
+        }
         a.fin.G = G;
         a.fin.M = (int)C;
         a.fin.nc_mode = engine->n_nc > 0;
@@ -853,6 +958,8 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             rc = engine->span_end(st);
             if (rc != SPADE_OK) return rc;
             engine->launches += 1;
+            rc = engine->fix_wide(st, 0, d_members, s0, Sb, 0, G, a.fin.fc, a.fin.cpm, a.fin.ld);
+            if (rc != SPADE_OK) return rc;
             CUDA_TRY(cudaStreamSynchronize(st));     // the host vectors above go out of scope
             if (host_out) {
                 for (int t = 0; t < 4; ++t)
@@ -871,6 +978,10 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             a.p1 = P;
             int rc = engine->launch_fused(a, false, st);
             if (rc != SPADE_OK) return rc;
+            if (!raw) {
+                rc = engine->fix_wide(st, 0, d_members, s0, Sb, 0, G, a.fin.fc, a.fin.cpm, a.fin.ld);
+                if (rc != SPADE_OK) return rc;
+            }
         } else {
             // Host outputs: strips of gene partitions, kernels alternating over two streams,
             // each finished strip copied out (2-D copy into the caller's [S][G] tables) while
@@ -884,6 +995,9 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
                 a.p0 = p0;
                 a.p1 = std::min(P, p0 + pg);
                 int rc = engine->launch_fused(a, false, ws);
+                if (rc != SPADE_OK) return rc;
+                rc = engine->fix_wide(ws, (int)(gi & 1), d_members, s0, Sb, (int64_t)a.p0 * engine->Gp,
+                                      std::min<int64_t>(G, (int64_t)a.p1 * engine->Gp), a.fin.fc, a.fin.cpm, a.fin.ld);
                 if (rc != SPADE_OK) return rc;
                 cudaEvent_t done;
                 rc = engine->sync_event(gi, &done);
@@ -947,15 +1061,52 @@ int spade_run_raw(spade_engine *engine, const int32_t *members, int members_loca
                     SPADE_DEVICE, out_row_stride, stream, (unsigned long long *)raw);
 }
 
+int spade_run_raw_blocks(spade_engine *engine, const int32_t *members, int members_location,
+                         const int64_t *offsets, int64_t S, const spade_gene_block *blocks, int nblocks,
+                         int64_t first_row, int64_t row_step, void *stream)
+{
+    if (!engine) return SPADE_ERR_ARG;
+    if (!blocks || nblocks < 1 || nblocks > kMaxGeneBlocks) { set_error("nblocks must be in [1, 16]"); return SPADE_ERR_ARG; }
+    if (first_row < 0 || row_step < 1) { set_error("first_row must be >= 0 and row_step >= 1"); return SPADE_ERR_ARG; }
+    int64_t at = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        const spade_gene_block &gb = blocks[b];
+        if (gb.gene_begin != at || gb.gene_end < gb.gene_begin || gb.gene_end > engine->G ||
+            (gb.gene_begin % engine->Gp) != 0 || (gb.gene_end > gb.gene_begin && (!gb.base || gb.ld < gb.gene_end - gb.gene_begin))) {
+            set_error("gene blocks must tile [0, G) in order, start on multiples of genes_per_part and have ld >= their width");
+            return SPADE_ERR_ARG;
+        }
+        at = gb.gene_end;
+    }
+    if (at != engine->G) { set_error("gene blocks must cover all G genes"); return SPADE_ERR_ARG; }
+    return run_impl(engine, members, members_location, offsets, S, nullptr, nullptr, nullptr, nullptr, nullptr,
+                    SPADE_DEVICE, engine->G, stream, (unsigned long long *)blocks[0].base /* marks the raw form */,
+                    blocks, nblocks, first_row, row_step);
+}
+
 int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_t raw_row_stride,
                  const int64_t *set_sizes, double *up, double *down, double *fc, double *cpm, int32_t *k,
                  int64_t out_row_stride, void *stream)
 {
     if (!engine) return SPADE_ERR_ARG;
+    return spade_expand_block(engine, raw, rows, raw_row_stride, 0, engine->G, set_sizes, up, down, fc, cpm, k,
+                              out_row_stride, stream);
+}
+
+int spade_expand_block(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_t raw_row_stride,
+                       int64_t gene_begin, int64_t gene_count, const int64_t *set_sizes, double *up,
+                       double *down, double *fc, double *cpm, int32_t *k, int64_t out_row_stride, void *stream)
+{
+    if (!engine) return SPADE_ERR_ARG;
     CUDA_TRY(cudaSetDevice(engine->device));
-    if (rows < 0 || !set_sizes || (rows > 0 && !raw)) { set_error("bad raw / rows / set_sizes"); return SPADE_ERR_ARG; }
-    if (raw_row_stride < engine->G || out_row_stride < engine->G) { set_error("row strides must be >= G"); return SPADE_ERR_ARG; }
-    if (rows == 0 || engine->G == 0) return SPADE_OK;
+    if (rows < 0 || !set_sizes || (rows > 0 && gene_count > 0 && !raw)) { set_error("bad raw / rows / set_sizes"); return SPADE_ERR_ARG; }
+    if (gene_begin < 0 || gene_count < 0 || gene_begin + gene_count > engine->G) { set_error("gene block out of range"); return SPADE_ERR_ARG; }
+    if (raw_row_stride < gene_count || out_row_stride < gene_count) { set_error("row strides must be >= the gene count of the block"); return SPADE_ERR_ARG; }
+    if (rows == 0 || gene_count == 0) return SPADE_OK;
+    if (!engine->h_wide.empty()) {
+        set_error("spade_expand is not available: the matrix holds genes that need the float64 side path");
+        return SPADE_ERR_STATE;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t G = engine->G;
     bool uniform = true;
@@ -997,14 +1148,29 @@ int spade_expand(spade_engine *engine, const uint64_t *raw, int64_t rows, int64_
         if (fr.fc) fr.fc += r0 * out_row_stride;
         if (fr.cpm) fr.cpm += r0 * out_row_stride;
         if (fr.k) fr.k += r0 * out_row_stride;
-        const dim3 grid((unsigned)((G + 255) / 256), (unsigned)((nr + kExpandRows - 1) / kExpandRows));
+        const dim3 grid((unsigned)((gene_count + 255) / 256), (unsigned)((nr + kExpandRows - 1) / kExpandRows));
         k_expand<<<grid, 256, 0, st>>>(fr, (const unsigned long long *)raw + r0 * raw_row_stride, raw_row_stride,
-                                       engine->sizes.p + r0, nr);
+                                       engine->sizes.p + r0, nr, gene_begin, gene_count);
         CUDA_TRY(cudaGetLastError());
     }
     rc = engine->span_end(st);
     if (rc != SPADE_OK) return rc;
     engine->launches += 1;
+    return SPADE_OK;
+}
+
+int spade_check(spade_engine *engine)
+{
+    if (!engine) return SPADE_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(engine->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return engine->check_device_error("spade_run");
+}
+
+int spade_wide_genes(const spade_engine *engine, int64_t *count)
+{
+    if (!engine || !count) return SPADE_ERR_ARG;
+    *count = (int64_t)engine->h_wide.size();
     return SPADE_OK;
 }
 
@@ -1208,6 +1374,109 @@ int spade_gamma_fit(int device, const double *table, int table_location, int64_t
     G_TRY(cudaMemcpy(C, dout.p + 2 * G, G * sizeof(double), cudaMemcpyDeviceToHost));
     if (status) G_TRY(cudaMemcpy(status, dst.p, G * sizeof(int32_t), cudaMemcpyDeviceToHost));
 #undef G_TRY
+    return SPADE_OK;
+}
+
+int spade_score(int device, const double *rand, int rand_location, int64_t S, int64_t G, int64_t rand_ld,
+                const double *obs, int obs_location, int64_t R, int64_t obs_ld, const double *A, const double *B,
+                const double *C, double *score, double *emp, int out_location, int64_t out_ld)
+{
+    auto fail = [&](int code, const std::string &m) { g_create_error = m; return code; };
+    const bool want_score = score && A && B && C, want_emp = emp && rand;
+    if (S < 0 || G < 0 || R < 0 || obs_ld < G || out_ld < G || (want_emp && rand_ld < G))
+        return fail(SPADE_ERR_ARG, "bad sizes / strides");
+    if ((score && !(A && B && C)) || (emp && !rand)) return fail(SPADE_ERR_ARG, "score needs A, B, C; emp needs the rand table");
+    if (want_emp && (S < 1 || S > kScoreMaxDraws)) return fail(SPADE_ERR_ARG, "the rand table must hold 1 .. 16384 draws");
+    for (int loc : {rand_location, obs_location, out_location})
+        if (loc != SPADE_HOST && loc != SPADE_DEVICE) return fail(SPADE_ERR_ARG, "bad location");
+    if (R == 0 || G == 0 || (!want_score && !want_emp)) return SPADE_OK;
+    if (!obs) return fail(SPADE_ERR_ARG, "obs is NULL");
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return fail(SPADE_ERR_CUDA, cudaGetErrorString(ce));
+#define S_TRY(expr)                                                                            \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return fail(SPADE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    DevBuf<double> drand, dobs, dabc, dsorted, dscore, demp;
+    DevBuf<int32_t> dvalid;
+    ScoreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.R = R; a.G = G; a.S = (int)S;
+    if (want_emp) {
+        const double *dr = rand;
+        int64_t ld = rand_ld;
+        if (rand_location == SPADE_HOST) {
+            S_TRY(drand.reserve((size_t)S * (size_t)G));
+            S_TRY(cudaMemcpy2D(drand.p, G * sizeof(double), rand, rand_ld * sizeof(double), G * sizeof(double), S,
+                               cudaMemcpyHostToDevice));
+            dr = drand.p;
+            ld = G;
+        }
+        S_TRY(dsorted.reserve((size_t)S * (size_t)G));
+        S_TRY(dvalid.reserve((size_t)G));
+        int m = 32;
+        while (m < S) m <<= 1;
+        const size_t smem = (size_t)m * sizeof(double);
+        S_TRY(cudaFuncSetAttribute(k_sort_background, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sort_background<<<(unsigned)G, 256, smem>>>(dr, (int)S, ld, dsorted.p, dvalid.p);
+        S_TRY(cudaGetLastError());
+        a.sorted = dsorted.p;
+        a.valid = dvalid.p;
+    }
+    a.obs = obs;
+    a.obs_ld = obs_ld;
+    if (obs_location == SPADE_HOST) {
+        S_TRY(dobs.reserve((size_t)R * (size_t)G));
+        S_TRY(cudaMemcpy2D(dobs.p, G * sizeof(double), obs, obs_ld * sizeof(double), G * sizeof(double), R,
+                           cudaMemcpyHostToDevice));
+        a.obs = dobs.p;
+        a.obs_ld = G;
+    }
+    if (want_score) {                                      // A, B, C: host vectors
+        S_TRY(dabc.reserve(3 * (size_t)G));
+        S_TRY(cudaMemcpy(dabc.p, A, G * sizeof(double), cudaMemcpyHostToDevice));
+        S_TRY(cudaMemcpy(dabc.p + G, B, G * sizeof(double), cudaMemcpyHostToDevice));
+        S_TRY(cudaMemcpy(dabc.p + 2 * G, C, G * sizeof(double), cudaMemcpyHostToDevice));
+        a.A = dabc.p; a.B = dabc.p + G; a.C = dabc.p + 2 * G;
+    }
+    a.score = want_score ? score : nullptr;
+    a.emp = want_emp ? emp : nullptr;
+    a.out_ld = out_ld;
+    if (out_location == SPADE_HOST) {
+        if (want_score) { S_TRY(dscore.reserve((size_t)R * (size_t)G)); a.score = dscore.p; }
+        if (want_emp) { S_TRY(demp.reserve((size_t)R * (size_t)G)); a.emp = demp.p; }
+        a.out_ld = G;
+    }
+    const dim3 grid((unsigned)((G + 255) / 256), (unsigned)std::min<int64_t>(R, 4096));
+    k_score<<<grid, 256>>>(a);
+    S_TRY(cudaGetLastError());
+    if (out_location == SPADE_HOST) {
+        if (want_score)
+            S_TRY(cudaMemcpy2D(score, out_ld * sizeof(double), dscore.p, G * sizeof(double), G * sizeof(double), R,
+                               cudaMemcpyDeviceToHost));
+        if (want_emp)
+            S_TRY(cudaMemcpy2D(emp, out_ld * sizeof(double), demp.p, G * sizeof(double), G * sizeof(double), R,
+                               cudaMemcpyDeviceToHost));
+    }
+    S_TRY(cudaDeviceSynchronize());
+#undef S_TRY
+    return SPADE_OK;
+}
+
+int spade_memcpy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width_bytes,
+                   int64_t rows, int device_to_host, void *stream)
+{
+    if (!dst || !src || width_bytes < 0 || rows < 0 || dst_pitch < width_bytes || src_pitch < width_bytes)
+        return SPADE_ERR_ARG;
+    if (width_bytes == 0 || rows == 0) return SPADE_OK;
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width_bytes, (size_t)rows,
+                                      device_to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice,
+                                      (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaMemcpy2DAsync: ") + cudaGetErrorString(e);
+        return SPADE_ERR_CUDA;
+    }
     return SPADE_OK;
 }
 

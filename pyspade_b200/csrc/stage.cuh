@@ -18,7 +18,7 @@ __global__ void k_col_sums(const int32_t *__restrict__ indices, const int32_t *_
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
          i += (int64_t)gridDim.x * blockDim.x) {
         int32_t c = indices[i];
-        if (c < 0 || c >= C) { atomicExch(err, 1); continue; }
+        if (c < 0 || c >= C) { flag_error(err, 1); continue; }
         atomicAdd(&colsum[c], (unsigned long long)(long long)counts[i]);
     }
 }
@@ -51,7 +51,7 @@ k_part_hist(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indi
     const bool dense = dslot[g] >= 0;             // lives in the dense block, not in a segment
     for (int64_t i = indptr[g] + threadIdx.x; i < indptr[g + 1]; i += blockDim.x) {
         const int32_t c = indices[i];
-        if (c < 0 || c >= C) { atomicExch(err, 1); continue; }
+        if (c < 0 || c >= C) { flag_error(err, 1); continue; }
         if (!dense) atomicAdd(&hist[base + c], 1u);
     }
 }
@@ -127,6 +127,7 @@ struct StageArgs {
     double *median;
     int32_t *n;
     GeneMeta *meta;
+    uint8_t *wide_flag;       // per gene: 1 = float64 side path (see the fixed-point comment below)
     int *err;
 };
 
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
 
     // pass 0: census of the scope, magnitude of the row
     long long in_scope = 0, neg = 0, pos = 0;
-    double rowabs = 0.0, maxabs = 0.0;
+    double rowabs = 0.0, maxabs = 0.0, minabs = INFINITY, bgd = 0.0;
     bool bad = false;
     for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
         const double v = a.values[i];
@@ -187,17 +188,21 @@ __global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
         bad |= !(av < 8.0e270);                   // nan, inf, or too large for the fixed point
         rowabs += av;
         maxabs = fmax(maxabs, av);
+        if (av > 0.0) minabs = fmin(minabs, av);
         if (a.ncmask && !a.ncmask[a.indices[i]]) continue;
         ++in_scope;
         neg += v < 0.0;
         pos += v > 0.0;
+        bgd += v;                                 // float64 NC sum (used by wide genes only)
     }
-    if (bad) atomicExch(a.err, 3);
+    if (bad) flag_error(a.err, 3);
     in_scope = block_sum(in_scope, scratch_ll);
     neg = block_sum(neg, scratch_ll);
     pos = block_sum(pos, scratch_ll);
     rowabs = block_sum(rowabs, scratch_d);
     maxabs = block_max(maxabs, scratch_d);
+    minabs = block_min(minabs, scratch_d);
+    bgd = block_sum(bgd, scratch_d);
     const int64_t L = a.scope_len;
     const int64_t implicit_zeros = L - in_scope;
     const int64_t zeros = L - neg - pos;            // implicit + explicitly stored zeros
@@ -216,13 +221,20 @@ __global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
 
     // Fixed point of this gene: any sum over <= kMemberBlock member cells stays below 2^46.
     //   bound = min(sum |v|, kMemberBlock * max |v|) < 2^e   ->   shift = 45 - e
+    // Every stored value is rounded to a multiple of 2^-shift, so a member mean is off by at most
+    // 2^-(shift+1); relative to a mean of same-signed values that is at most
+    // 2^-(shift+1) / min|nonzero value|.  Where this bound exceeds kWideRelBound (a few huge cells
+    // next to tiny ones) the gene is marked WIDE: its member and background means are summed in
+    // float64 by k_wide_means instead (the counts k stay with the packed flags, they are exact).
     int shift = 0;
+    bool wide = false;
     {
         const double bound = fmin(rowabs, (double)kMemberBlock * maxabs);
         if (bound > 0.0 && !bad) {
             int e;
             frexp(bound, &e);
             shift = min(900, max(-900, 45 - e));
+            wide = !(scalbn(minabs, shift + 1) * kWideRelBound >= 1.0);
         }
     }
 
@@ -261,10 +273,12 @@ __global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
         mt.n = n;
         mt.shift = (int16_t)shift;
         mt.negmode = negmode ? 1 : 0;
-        mt.pad = 0;
-        if (a.ncmask) mt.bgmean = ((double)bgsum * pow2_double(-shift)) * (1.0 / (double)L);
+        mt.wide = wide ? 1 : 0;
+        if (a.ncmask) mt.bgmean = wide ? bgd * (1.0 / (double)L)
+                                       : ((double)bgsum * pow2_double(-shift)) * (1.0 / (double)L);
         else mt.rowsum = rowsum;
         a.meta[g] = mt;
+        a.wide_flag[g] = wide ? 1 : 0;
     }
 }
 

@@ -332,6 +332,62 @@ class Engine:
                                            dp(out.get("fc")), dp(out.get("cpm")), dp(k),
                                            int(row_stride or self.G), ctypes.c_void_p(stream.cuda_stream)))
 
+    def run_raw_blocks(self, members, offsets_host, blocks, first_row=0, row_step=1, stream=None):
+        """``spade_run_raw_blocks``: raw words routed by gene block.  ``members``: int32 torch
+        tensor on this GPU, or a numpy array (uploaded by the call).  ``blocks``: list of
+        ``(device address, ld, gene_begin, gene_end)``, one per owner, tiling ``[0, G)``."""
+        import torch
+
+        offsets = np.ascontiguousarray(offsets_host, dtype=np.int64)
+        S = offsets.shape[0] - 1
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        arr = (_lib.GeneBlock * len(blocks))()
+        for i, (base, ld, g0, g1) in enumerate(blocks):
+            arr[i].base, arr[i].ld, arr[i].gene_begin, arr[i].gene_end = int(base), int(ld), int(g0), int(g1)
+        if isinstance(members, np.ndarray):
+            members = np.ascontiguousarray(members, dtype=np.int32)
+            mp, loc = _ptr(members), _lib.SPADE_HOST
+        else:
+            assert members.dtype == torch.int32
+            mp, loc = ctypes.c_void_p(members.data_ptr()), _lib.SPADE_DEVICE
+        self._check(self._lib.spade_run_raw_blocks(self._h, mp, loc, _ptr(offsets), S, arr, len(blocks),
+                                                   int(first_row), int(row_step),
+                                                   ctypes.c_void_p(stream.cuda_stream)))
+
+    def expand_block(self, raw, set_sizes, gene_begin, gene_count, out, k=None, raw_row_stride=None,
+                     row_stride=None, stream=None):
+        """``spade_expand_block``: finish ``len(set_sizes)`` rows x ``gene_count`` words (column j
+        = gene ``gene_begin + j``) into the tables of ``out`` (torch tensors or device addresses)."""
+        import torch
+
+        sizes = np.ascontiguousarray(set_sizes, dtype=np.int64)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+
+        def dp(t):
+            if t is None:
+                return None
+            return ctypes.c_void_p(t if isinstance(t, int) else t.data_ptr())
+
+        self._check(self._lib.spade_expand_block(
+            self._h, dp(raw), sizes.shape[0], int(raw_row_stride or gene_count), int(gene_begin), int(gene_count),
+            _ptr(sizes), dp(out.get("up")), dp(out.get("down")), dp(out.get("fc")), dp(out.get("cpm")), dp(k),
+            int(row_stride or gene_count), ctypes.c_void_p(stream.cuda_stream)))
+
+    def check(self):
+        """``spade_check``: wait for the device and raise what the runs issued so far flagged
+        (``IndexError`` for a member cell out of range, ``ValueError`` for a duplicated cell) -
+        ``run_device`` / ``run_raw`` return before their kernels have run."""
+        self._check(self._lib.spade_check(self._h))
+
+    @property
+    def wide_genes(self):
+        """Number of genes whose means take the float64 side path (``spade_wide_genes``)."""
+        n = ctypes.c_int64()
+        self._check(self._lib.spade_wide_genes(self._h, ctypes.byref(n)))
+        return n.value
+
     def timing(self, reset=False):
         a, f, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
         self._check(self._lib.spade_timing(self._h, ctypes.byref(a), ctypes.byref(f),

@@ -1,11 +1,21 @@
 """Sharding of cell sets over the GPUs of one node.
 
 Every (gene, set) test is independent, so DErand shards by draw and DEobs by region: the
-staged matrix is replicated on every GPU, each rank runs its own sets, and one gather of the
-per-set result tables to rank 0 is the only communication (NCCL over NVLink for device
-tensors, gloo for the CPU tests).  Sets are always generated / enumerated on every rank in
-the same global order before they are split, so the tables do not depend on the number of
-ranks: sums are integer, tails are a pure function of (k, M, n, N).
+staged matrix is replicated on every GPU and each rank tests its own sets.  Sets are always
+generated / enumerated on every rank in the same global order before they are split, so the
+tables do not depend on the number of ranks: sums are integer, tails are a pure function of
+(k, M, n, N).  What happens to the results:
+
+* :class:`GeneExchange` / :func:`run_gene_sharded` - tables stay on the GPUs, re-sharded by
+  GENE: the test kernel stores its raw 8-byte accumulator words straight into the memory of
+  the GPU that owns the gene block (CUDA IPC over NVLink / NVSwitch, an all-to-all fused into
+  the kernel), and every GPU finishes ALL sets x ITS genes (``spade_expand_block``).  No GPU
+  is a funnel, and the layout is the one the per-gene consumers need (gamma fit over the
+  draws, empirical p-values, column-compressed MAT tables).
+* :func:`run_sharded` - tables wanted on the host of rank 0: every rank delivers its rows over
+  its own PCIe link into host tables shared by the node (``gather="host"``), or one NCCL
+  gather per table over NVLink (``gather="nccl"``, what north_star names; gloo in the CPU
+  tests).
 """
 import ctypes
 import os
@@ -40,22 +50,15 @@ def plan(sizes, world_size, balance=False):
     return [np.flatnonzero(owner == r).astype(np.int64) for r in range(world_size)]
 
 
-def expander_shares(total_sets, world_size, expand_cost=0.12):
-    """Contiguous shares of ``total_sets`` for the raw-word gather, where rank 0 also expands
-    the words of all other ranks (``spade_expand``, about ``expand_cost`` of the cost of
-    testing a set): rank 0 takes fewer sets so that every rank finishes together,
-        x (1 - e) + T e = (T - x) / (P - 1),   T = total_sets, e = expand_cost.
-    Returns ``counts`` (list, rank 0 first); the ranks > 0 get equal counts."""
-    P, T, e = world_size, total_sets, expand_cost
-    if P <= 1:
-        return [T]
-    x = T * (1.0 / (P - 1) - e) / (1.0 - e + 1.0 / (P - 1))
-    y = int(np.ceil((T - max(x, 0.0)) / (P - 1)))
-    x = T - y * (P - 1)
-    while x < 0:                                       # tiny T: give the remainder to the peers
-        y -= 1
-        x = T - y * (P - 1)
-    return [x] + [y] * (P - 1)
+def gene_blocks(G, genes_per_part, world_size):
+    """Gene range owned by each of ``world_size`` ranks in the gene-sharded exchange: consecutive
+    runs of whole gene partitions of the staged layout, as even as the partition count allows.
+    List of ``(gene_begin, gene_end)``; a rank may own nothing when there are fewer partitions
+    than ranks."""
+    nparts = (G + genes_per_part - 1) // genes_per_part
+    cuts = [(q * nparts) // world_size for q in range(world_size + 1)]
+    return [(min(G, cuts[q] * genes_per_part), min(G, cuts[q + 1] * genes_per_part))
+            for q in range(world_size)]
 
 
 def gather_rows(local, assignment, rank, world_size, n_cols, group=None):
@@ -93,83 +96,178 @@ def gather_rows(local, assignment, rank, world_size, n_cols, group=None):
     return out
 
 
-class PeerTables:
-    """Result tables that live in rank 0's HBM and are mapped into every rank of the node.
+class PeerBuffers:
+    """``count`` device buffers of ``nbytes`` in EVERY rank's HBM, each mapped into every rank of
+    the node: rank r allocates its own (``spade_device_alloc``), exports CUDA IPC handles, and
+    opens everybody else's (``spade_ipc_open``, peer access over NVLink / NVSwitch).
+    ``ptr[i][r]`` is the address, valid in this process, of buffer ``i`` of rank ``r``.
+    ``torch.distributed`` carries the 64-byte handles."""
 
-    Rank 0 allocates ``rows x cols`` elements per table (``spade_device_alloc``), exports
-    CUDA IPC handles, the other ranks open them (``spade_ipc_open``, peer access over
-    NVLink / NVSwitch).  A rank passes ``address(name, first_row)`` to
-    ``Engine.run_device(..., row_stride=...)``: the test kernel then stores its results
-    directly into rank 0's memory while it computes - the gather is fused into the kernel and
-    needs no collective, only a barrier before rank 0 reads.  ``torch.distributed`` is used for
-    the handle exchange and the barrier."""
-
-    ITEM = {"up": 8, "down": 8, "fc": 8, "cpm": 8, "k": 4, "raw": 8}
-
-    def __init__(self, names, rows, cols, rank, world_size, device):
+    def __init__(self, nbytes, rank, world_size, device, count=1):
         import torch.distributed as dist
 
         from . import _lib
         self._lib = _lib.load()
-        self.names, self.rows, self.cols = list(names), int(rows), int(cols)
-        self.rank, self.device = rank, device
-        self.ptr = {}
-        handles = [None]
-        if rank == 0:
-            try:
-                hs = {}
-                for name in self.names:
-                    p = ctypes.c_void_p()
-                    self._ok(self._lib.spade_device_alloc(device, ctypes.byref(p),
-                                                          self.rows * self.cols * self.ITEM[name]))
-                    self.ptr[name] = p.value
-                    buf = ctypes.create_string_buffer(64)
-                    self._ok(self._lib.spade_ipc_export(device, p, buf))
-                    hs[name] = bytes(buf.raw)
-                handles = [hs]
-            except RuntimeError as exc:                # every rank must leave the broadcast together
-                handles = [str(exc)]
-        dist.broadcast_object_list(handles, src=0)
-        if isinstance(handles[0], str):
-            self.close()
-            raise RuntimeError(handles[0])
-        if rank != 0:
-            for name in self.names:
+        self.rank, self.world, self.device, self.nbytes = rank, world_size, device, int(nbytes)
+        self.ptr = [[None] * world_size for _ in range(count)]
+        mine, err = [], None
+        try:
+            for i in range(count):
                 p = ctypes.c_void_p()
-                self._ok(self._lib.spade_ipc_open(device, handles[0][name], ctypes.byref(p)))
-                self.ptr[name] = p.value
+                self._ok(self._lib.spade_device_alloc(device, ctypes.byref(p), self.nbytes))
+                self.ptr[i][rank] = p.value
+                buf = ctypes.create_string_buffer(64)
+                self._ok(self._lib.spade_ipc_export(device, p, buf))
+                mine.append(bytes(buf.raw))
+        except RuntimeError as exc:                    # every rank must reach the exchange
+            err = str(exc)
+        everyone = [None] * world_size
+        dist.all_gather_object(everyone, err if err else mine)
+        bad = [e for e in everyone if isinstance(e, str)]
+        try:
+            if bad:
+                raise RuntimeError(bad[0])
+            for r in range(world_size):
+                if r == rank:
+                    continue
+                for i in range(count):
+                    p = ctypes.c_void_p()
+                    self._ok(self._lib.spade_ipc_open(device, everyone[r][i], ctypes.byref(p)))
+                    self.ptr[i][r] = p.value
+        except RuntimeError:
+            self.close()
+            raise
 
     def _ok(self, rc):
         if rc != 0:
-            raise RuntimeError("peer tables: " + self._lib.spade_last_error(None).decode())
-
-    def address(self, name, first_row=0, first_col=0):
-        return self.ptr[name] + (first_row * self.cols + first_col) * self.ITEM[name]
-
-    def tensor(self, name):
-        """Rank 0: the table as a torch tensor (no copy)."""
-        import torch
-
-        assert self.rank == 0
-        dtype, typestr = {"k": (torch.int32, "<i4"), "raw": (torch.int64, "<i8")}.get(name, (torch.float64, "<f8"))
-
-        class _View:
-            pass
-
-        v = _View()
-        v.__cuda_array_interface__ = {"shape": (self.rows, self.cols), "typestr": typestr,
-                                      "data": (self.ptr[name], False), "version": 2}
-        t = torch.as_tensor(v, device=torch.device("cuda", self.device))
-        assert t.dtype == dtype
-        return t
+            raise RuntimeError("peer buffers: " + self._lib.spade_last_error(None).decode())
 
     def close(self):
-        for name, p in self.ptr.items():
-            if self.rank == 0:
-                self._lib.spade_device_free(self.device, ctypes.c_void_p(p))
-            else:
-                self._lib.spade_ipc_close(self.device, ctypes.c_void_p(p))
-        self.ptr = {}
+        for row in self.ptr:
+            for r, p in enumerate(row):
+                if p is None:
+                    continue
+                if r == self.rank:
+                    self._lib.spade_device_free(self.device, ctypes.c_void_p(p))
+                else:
+                    self._lib.spade_ipc_close(self.device, ctypes.c_void_p(p))
+        self.ptr = []
+
+
+class GeneExchange:
+    """Multi-GPU form of the batched test with the tables re-sharded by gene (see the module
+    docstring).  One object per rank and engine; ``max_rows`` = the largest number of sets (over
+    ALL ranks) of one step.
+
+    ``step(members, offsets, first_row, row_step, set_sizes)`` is asynchronous: the routed raw
+    launch and a 4-byte NCCL all-reduce ("every rank's words have landed") go on the current
+    stream, the expansion of this rank's gene block on a side stream, so that the test kernel of
+    the next step overlaps it.  Two word buffers are used in turn; the expansion of step i is
+    waited for before this rank enters the all-reduce of step i + 1, which is what allows the
+    peers to overwrite that buffer in step i + 2.  ``drain()`` makes the current stream wait for
+    the last expansion; then ``tables[name][:rows]`` holds ALL sets x the genes
+    ``[gene_begin, gene_end)`` of this rank, rows in global set order."""
+
+    def __init__(self, engine, max_rows, tables=("up", "down", "cpm"), want_k=False, rank=None,
+                 world_size=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        r, lr, P = world()
+        self.rank = r if rank is None else rank
+        self.world = P if world_size is None else world_size
+        self.device = lr if device is None else device
+        self.engine, self.max_rows = engine, int(max_rows)
+        if engine.wide_genes:
+            raise RuntimeError("gene-sharded exchange needs the raw form, which this matrix cannot use "
+                               "(wide genes, see spade_wide_genes); use run_sharded(gather='host')")
+        self.blocks = gene_blocks(engine.G, engine.genes_per_part, self.world)
+        self.gene_begin, self.gene_end = self.blocks[self.rank]
+        self.width = max(1, max(b - a for a, b in self.blocks))
+        self.words = PeerBuffers(self.max_rows * self.width * 8, self.rank, self.world, self.device, count=2)
+        dev = torch.device("cuda", self.device)
+        cols = max(1, self.gene_end - self.gene_begin)
+        self.cols = cols
+        self.tables = {n: torch.empty((self.max_rows, cols), dtype=torch.float64, device=dev) for n in tables}
+        self.k = torch.empty((self.max_rows, cols), dtype=torch.int32, device=dev) if want_k else None
+        self.side = torch.cuda.Stream(device=dev)
+        self.flag = torch.zeros(1, device=dev)
+        self.expanded = None
+        self.steps = 0
+        self._dist = dist
+
+    def step(self, members, offsets, first_row, row_step, set_sizes):
+        import torch
+
+        rows = len(set_sizes)
+        assert rows <= self.max_rows
+        buf = self.steps & 1
+        self.steps += 1
+        main = torch.cuda.current_stream(self.device)
+        blocks = [(self.words.ptr[buf][q], self.width, a, b) for q, (a, b) in enumerate(self.blocks)]
+        if len(offsets) > 1:
+            self.engine.run_raw_blocks(members, offsets, blocks, first_row, row_step, stream=main)
+        if self.expanded is not None:
+            main.wait_event(self.expanded)
+        self._dist.all_reduce(self.flag)               # passes once every rank's kernel has finished
+        landed = torch.cuda.Event()
+        landed.record(main)
+        self.side.wait_event(landed)
+        if self.gene_end > self.gene_begin and rows:
+            self.engine.expand_block(self.words.ptr[buf][self.rank], set_sizes, self.gene_begin,
+                                     self.gene_end - self.gene_begin, self.tables, k=self.k,
+                                     raw_row_stride=self.width, row_stride=self.cols, stream=self.side)
+        self.expanded = torch.cuda.Event()
+        self.expanded.record(self.side)
+        self.rows = rows
+
+    def drain(self):
+        import torch
+        if self.expanded is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.expanded)
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize(self.device)
+        self.words.close()
+        self.tables = {}
+
+
+def run_gene_sharded(engine, sets, tables=("up", "down", "cpm"), balance=False, want_k=False, exchange=None):
+    """Test ``sets`` over all ranks and leave the tables ON THE GPUS, sharded by gene.
+
+    Returns ``(exchange, order)``: ``exchange.tables[name][:len(sets)]`` is a CUDA tensor
+    ``[S, gene_end - gene_begin]`` of this rank's gene block; ``order[i]`` = index in ``sets`` of
+    table row ``i`` (identity for round-robin sharding; with ``balance=True`` the rows are grouped
+    by the rank that tested them).  Pass ``exchange`` to reuse the buffers of an earlier call."""
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, P = world()
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sizes = np.array([len(s) for s in sets], dtype=np.int64)
+    assignment = plan(sizes, P, balance=balance)
+    mine = [sets[i] for i in assignment[rank]]
+    members, offsets = engine.pack_sets(mine)
+    S = len(sets)
+    if exchange is None:
+        exchange = GeneExchange(engine, S, tables=tables, want_k=want_k)
+    if balance:
+        order = np.concatenate(assignment)
+        first_row, row_step = int(sum(len(a) for a in assignment[:rank])), 1
+    else:
+        order = np.arange(S, dtype=np.int64)
+        first_row, row_step = rank, P
+    exchange.step(members.astype(np.int32), offsets, first_row, row_step, sizes[order])
+    exchange.drain()
+    failure = None
+    try:
+        engine.check()
+    except Exception as exc:                               # noqa: BLE001
+        failure = exc
+    _raise_together(failure, rank)
+    return exchange, order
 
 
 class _near_gpu:
@@ -277,6 +375,21 @@ class SharedHostTables:
 _SHARED = {}
 
 
+def _raise_together(failure, rank):
+    """Collective: every rank learns whether any rank failed, and all raise together (a bare
+    barrier would leave the healthy ranks waiting forever for the one that raised)."""
+    import torch
+    import torch.distributed as dist
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    bad = torch.tensor([0 if failure is None else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    if failure is not None:
+        raise failure
+    if int(bad) != 0:
+        raise RuntimeError(f"rank {rank}: another rank failed while running its share of the sets")
+
+
 def _shared_tables(names, rows, cols, rank, world_size, touch=None):
     """One set of shared host tables per (names, cols), grown when more rows are needed."""
     key = (tuple(names), cols)
@@ -284,6 +397,7 @@ def _shared_tables(names, rows, cols, rank, world_size, touch=None):
     if cur is not None and cur.rows >= rows:
         return cur
     if cur is not None:
+        _SHARED.pop(key)                 # a failed regrow must not leave a closed object behind
         cur.close()
     _SHARED[key] = SharedHostTables(names, rows, cols, rank, world_size, touch=touch, device=world()[1])
     return _SHARED[key]
@@ -333,10 +447,14 @@ def run_sharded(engine, sets, tables=("up", "down", "fc", "cpm"), balance=False,
         else:              # round-robin: set i of rank r is row i*P + r
             out = {n: shared.rows_view(n, rank, P, len(mine)) for n in names}
             stride = P * G
-        if len(mine):
-            engine.run(members=members, offsets=offsets, out=out, tables=tables, want_k=want_k,
-                       row_stride=stride)
-        dist.barrier()
+        failure = None
+        try:
+            if len(mine):
+                engine.run(members=members, offsets=offsets, out=out, tables=tables, want_k=want_k,
+                           row_stride=stride)
+        except Exception as exc:                         # noqa: BLE001 - re-raised on every rank below
+            failure = exc
+        _raise_together(failure, rank)                   # also the barrier: all rows are in place
         res = None
         if rank == 0:
             if balance:

@@ -92,3 +92,33 @@ def concat_sets(sets):
     members = (np.concatenate([np.asarray(s, dtype=np.int32) for s in sets])
                if len(sets) else np.zeros(0, np.int32))
     return np.ascontiguousarray(members, dtype=np.int32), offsets
+
+
+def sample_rows(indptr, indices, counts, G, C, n_genes):
+    """Host float64 CPM rows of a density-stratified gene sample of a device-resident count
+    matrix (torch CSR as returned by ``counts_torch``): genes evenly spaced over the order by
+    number of expressing cells, values in the reference's CPM operation order
+    (``utils.py:150-155``).  Returns ``(gene ids ascending, scipy CSR [len(ids), C])`` - what
+    the CPU oracle is fed when the full matrix is too large for it."""
+    import torch
+
+    nnz_g = (indptr[1:] - indptr[:-1])
+    order = torch.argsort(nnz_g, stable=True)
+    pick = order[torch.linspace(0, G - 1, n_genes, device=order.device).round().long()]
+    pick = torch.unique(pick)                      # sorted, unique gene ids
+    lens = nnz_g[pick]
+    starts = indptr[:-1][pick]
+    sub_ptr = torch.zeros(pick.numel() + 1, dtype=torch.int64, device=pick.device)
+    sub_ptr[1:] = torch.cumsum(lens, 0)
+    pos = torch.arange(int(sub_ptr[-1]), device=pick.device)
+    row = torch.repeat_interleave(torch.arange(pick.numel(), device=pick.device), lens)
+    src = starts[row] + (pos - sub_ptr[:-1][row])
+    colsum = torch.zeros(C, dtype=torch.int64, device=pick.device)
+    colsum.index_add_(0, indices.long(), counts.long())
+    sub_idx = indices[src].cpu().numpy()
+    sub_cnt = counts[src].cpu().numpy()
+    with np.errstate(divide="ignore"):
+        inv = 1.0 / colsum.cpu().numpy()
+    data = (sub_cnt.astype(np.float64) * 1e6) * inv[sub_idx]        # utils.py:150-155 order
+    X = sp.csr_matrix((data, sub_idx, sub_ptr.cpu().numpy()), shape=(pick.numel(), C))
+    return pick.cpu().numpy(), X

@@ -130,31 +130,56 @@ def region_cell_sets(sgrna_df_bool, sgrna_dict, skip=(), logger=None):
 # ------------------------------------------------------------------------------------------
 # staged matrices: one engine per input matrix object, kept while the matrix is alive
 # ------------------------------------------------------------------------------------------
-_ENGINES = {}
+_ENGINES = {}          # id(matrix) -> (weakref to the matrix, engine, fingerprint)
+
+
+def _fingerprint(matrix):
+    """Cheap guard against in-place edits of a cached matrix (the reference re-reads the
+    matrix on every call): shape, nnz and a strided sample of the stored values."""
+    data = getattr(matrix, "data", None)
+    if not isinstance(data, np.ndarray):
+        return None
+    step = max(1, data.shape[0] // 4096)
+    sample = data[::step]
+    return (tuple(matrix.shape), int(data.shape[0]), float(np.nansum(sample)), int(np.isnan(sample).sum()))
 
 
 def _drop_engine(key):
-    eng = _ENGINES.pop(key, None)
-    if eng is not None:
-        eng[0].close()
+    hit = _ENGINES.pop(key, None)
+    if hit is not None:
+        hit[1].close()
 
 
 def _remember(matrix, engine):
-    key = id(matrix)
-    _ENGINES[key] = (engine, None)
+    """Keep ``engine`` for as long as ``matrix`` lives.  Objects that cannot be weakly
+    referenced are not cached at all (``id()`` values are recycled)."""
     try:
+        ref = weakref.ref(matrix)
+        key = id(matrix)
         weakref.finalize(matrix, _drop_engine, key)
     except TypeError:
-        pass
+        return engine
+    _ENGINES[key] = (ref, engine, _fingerprint(matrix))
     return engine
 
 
 def engine_for(input_array, device=0):
-    """The engine staged for this matrix object (staged on first use)."""
-    hit = _ENGINES.get(id(input_array))
+    """The engine staged for this matrix object (staged on first use).  The cache entry is
+    used only when it was made for this very object and the stored values still look the same;
+    the matrix must not be edited in place between calls."""
+    key = id(input_array)
+    hit = _ENGINES.get(key)
     if hit is not None:
-        return hit[0]
+        if hit[0]() is input_array and hit[2] == _fingerprint(input_array):
+            return hit[1]
+        _drop_engine(key)
     return _remember(input_array, Engine.from_cpm(input_array, device=device))
+
+
+def _release_if_uncached(input_array, eng):
+    hit = _ENGINES.get(id(input_array))
+    if hit is None or hit[1] is not eng:
+        eng.close()
 
 
 def cpm_normalization(trans_df, device=0):
@@ -200,6 +225,7 @@ def perform_DE(sgrna_idx, input_array, idx, num_processes, pval_list_down, pval_
     res = eng.run([np.asarray(sgrna_idx, dtype=np.int64)])
     pval_list_down, pval_list_up, fc_list, cpm_list = map(_as_out, (pval_list_down, pval_list_up,
                                                                     fc_list, cpm_list))
+    _release_if_uncached(input_array, eng)
     _scatter(idx, res, pval_list_down, pval_list_up, fc_list, cpm_list)
     return len(sgrna_idx), pval_list_up, pval_list_down, fc_list, cpm_list
 
@@ -214,5 +240,6 @@ def perform_DE_NC(sgrna_idx, NC_idx, input_array, idx, num_processes, pval_list_
     res = eng.run([np.asarray(sgrna_idx, dtype=np.int64)])
     pval_list_down, pval_list_up, fc_list, cpm_list = map(_as_out, (pval_list_down, pval_list_up,
                                                                     fc_list, cpm_list))
+    _release_if_uncached(input_array, eng)
     _scatter(idx, res, pval_list_down, pval_list_up, fc_list, cpm_list)
     return len(sgrna_idx), pval_list_up, pval_list_down, fc_list, cpm_list

@@ -14,7 +14,7 @@ def _declared_symbols():
     with open(os.path.join(ROOT, "include", "spade.h")) as fh:
         text = fh.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(spade_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(spade_[a-z_0-9]+)\s*\(", text)))
 
 
 def test_header_symbols_exported():

@@ -277,15 +277,14 @@ def test_mat_writers_load_like_scipy_written_files(tmp_path):
     assert np.array_equal(np.asarray(sio.loadmat(str(tmp_path / "p2"))["matrix"].todense()), -t + 0.0, equal_nan=True)
 
 
-def test_expander_shares_balance_and_cover():
-    """Rank 0 expands everybody's raw words (cost e per set): x(1-e) + T e = (T - x)/(P - 1)."""
-    assert shard.expander_shares(1000, 1) == [1000]
-    for P in (2, 3, 4, 8):
-        T = 1000 * P
-        c = shard.expander_shares(T, P, expand_cost=0.12)
-        assert sum(c) == T and len(c) == P and min(c) >= 0 and len(set(c[1:])) == 1
-        rank0 = c[0] + 0.12 * (T - c[0])                # its own tests + the expansion of the others
-        assert abs(rank0 - c[1]) <= P                    # finishes together with the peers (integer shares)
-    assert shard.expander_shares(3, 4) == [0, 1, 1, 1] and shard.expander_shares(0, 2) == [0, 0]
-    with shard._near_gpu(None):                          # no device: a no-op
-        pass
+def test_gene_blocks_tile_all_genes_on_partition_boundaries():
+    from pyspade_b200 import shard
+    for G, Gp in ((33000, 1024), (1000, 1024), (5000, 96), (64, 32), (0, 1024)):
+        for P in (1, 2, 3, 4, 8, 16):
+            blocks = shard.gene_blocks(G, Gp, P)
+            assert len(blocks) == P and blocks[0][0] == 0 and blocks[-1][1] == G
+            for (a, b), (c, d) in zip(blocks, blocks[1:]):
+                assert b == c and a <= b
+            assert all(a % Gp == 0 for a, b in blocks if b > a)
+            widths = [b - a for a, b in blocks]
+            assert max(widths) - min(widths) <= Gp                 # as even as whole partitions allow
