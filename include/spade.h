@@ -235,6 +235,23 @@ int spade_expand_block(spade_engine *engine, const uint64_t *raw, int64_t rows, 
                        int64_t gene_begin, int64_t gene_count, const int64_t *set_sizes, double *up,
                        double *down, double *fc, double *cpm, int32_t *k, int64_t out_row_stride, void *stream);
 
+/*
+ * Wire format of the DErand tables, built on the GPU (pySpade/DErand.py:230-248 saves each
+ * table with scipy.io.savemat(csr_matrix(dense)): a MAT-v5 sparse array, column-compressed with
+ * column = gene; stored entries are those != 0 - nan and -inf are stored, +-0.0 are not).
+ * table: DEVICE float64 [S][ld], first G columns (all draws x a block of genes).
+ *   spade_csc_count  jc[G+1] (HOST int32): jc[0] = 0, jc[g+1] = stored entries of columns 0..g
+ *   spade_csc_fill   ir[nnz] row (draw) indices, ascending inside a column, and pr[nnz] values,
+ *                    nnz = jc[G] - jc[0]; host or device per out_location
+ * so that the host only writes headers and these arrays (pyspade_b200/io.py), and the dense
+ * tables never cross PCIe.  spade_column_mean: mean over the S rows of every column (host
+ * float64[G]), DErand.py:252's Cpm_mean.  All three synchronise.
+ */
+int spade_csc_count(int device, const double *table, int64_t S, int64_t G, int64_t ld, int32_t *jc);
+int spade_csc_fill(int device, const double *table, int64_t S, int64_t G, int64_t ld, const int32_t *jc,
+                   int32_t *ir, double *pr, int out_location);
+int spade_column_mean(int device, const double *table, int64_t S, int64_t G, int64_t ld, double *mean);
+
 /* Strided copy between device and host memory on a stream (cudaMemcpy2DAsync): a gene block
  * [rows][width] of a device table into / out of a wider host table. */
 int spade_memcpy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width_bytes,

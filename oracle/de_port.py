@@ -273,6 +273,17 @@ def de_tables(X, sets, nc_idx=None, tail_fn=None):
             # every stored value inside the set -> the rest is exactly zero
             nnz_g = np.diff(X.indptr)
             rest = np.where(any_hits == nnz_g[None, :], 0.0, rest)
+            # rowsum - sums cancels when the set holds nearly all of a row's mass (rows with a few
+            # huge cells): those entries are summed directly over the complement, as the
+            # reference does (utils.py:206-207)
+            abs_rowsum = np.asarray(abs(X).sum(axis=1)).ravel()
+            risky = np.abs(rowsum[None, :] - sums) < 1e-5 * abs_rowsum[None, :]
+            risky &= any_hits != nnz_g[None, :]
+            for s_i, g_i in zip(*np.nonzero(risky)):
+                row = np.asarray(X[g_i].todense()).ravel()
+                outside = np.ones(C, dtype=bool)
+                outside[np.asarray(sets[s_i], dtype=np.int64)] = False
+                rest[s_i, g_i] = _mean_like_scipy_sparse(row[outside], C - int(N[s_i]))
         else:
             nc = np.asarray(nc_idx, dtype=np.int64)
             bg = np.asarray(X[:, nc].sum(axis=1)).ravel() * (1.0 / nc.shape[0])

@@ -76,9 +76,19 @@ def DE_observe_cells(sub_df_file,
         skip = (background_cells,)
 
     regions = region_cell_sets(sgrna_df_adj_bool, sgrna_dict, skip=skip, logger=logger)
+    pinned = None
+    if world == 1 and regions:
+        # one set of page-locked host tables, reused by every batch (fast device->host copies)
+        from .engine import PinnedArray
+        rows = min(REGION_BATCH, len(regions))
+        pinned = {n: PinnedArray((rows, g), np.float64) for n in ("up", "down", "fc", "cpm")}
     for b0 in range(0, len(regions), REGION_BATCH):
         batch = regions[b0:b0 + REGION_BATCH]
-        res = shard.run_sharded(engine, [cells for _, cells in batch], balance=True)
+        sets = [cells for _, cells in batch]
+        if pinned is not None:
+            res = engine.run(sets, out={n: p.array[:len(sets)] for n, p in pinned.items()})
+        else:
+            res = shard.run_sharded(engine, sets, balance=True)
         if rank != 0:
             continue
         for j, (k, cells) in enumerate(batch):
@@ -88,6 +98,10 @@ def DE_observe_cells(sub_df_file,
             spio.save_vector('%s/%s-%s-foldchange' % (output_dir, k, num_sgrna_cell), res["fc"][j])
             spio.save_vector('%s/%s-cpm' % (output_dir, k), res["cpm"][j])
     engine.close()
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
     logger.info('Job is done.')
 
 

@@ -60,11 +60,15 @@ def gamma_parameters(table, what, processes=None, min_pool_work=200000):
 
 def gamma_parameters_device(table, what, device=0):
     """The same tail on the GPU (``spade_gamma_fit``: scipy's start values, penalised likelihood
-    and Nelder-Mead restated in ``csrc/gamma_fit.cuh``, one gene per thread) - seconds instead
-    of minutes for 2 x 33 000 fits.  Parameters agree with scipy's to the optimiser's tolerance
-    wherever its optimum is stable (``tests/test_gamma_fit.py``)."""
+    and Nelder-Mead restated in ``csrc/gamma_fit.cuh``, one gene per warp) - a fraction of a
+    second instead of minutes for 2 x 33 000 fits.  Opt-in (``--gamma_fit device``): the
+    3-parameter likelihood is ill-conditioned for genes with few distinct values, and there the
+    simplex of this implementation and scipy's end at different points (see DESIGN.md for the
+    measured agreement); where scipy would raise ``FitError`` nan is written."""
     from .engine import gamma_fit
     A, B, C, status = gamma_fit(table, sign=-1.0, device=device)
+    logger.info(f'{what}: {int(np.count_nonzero(status == 0))} genes fitted on the GPU, '
+                f'{int(np.count_nonzero(status == 1))} skipped, {int(np.count_nonzero(status == 2))} constant.')
     bad = int(np.count_nonzero(status == 3))
     if bad:
         logger.critical(f'{bad} genes: the {what} gamma fit did not converge to valid parameters (nan written).')
@@ -150,27 +154,131 @@ def DE_random_cells(sub_df_file,
         else:
             draws.append(np.random.choice(population, size=num_cell, replace=False))
 
-    res = shard.run_sharded(engine, draws, tables=("up", "down", "cpm"))
-    engine.close()
-    if rank != 0:
-        return
-
-    spio.write_cell_ids(output_dir + '/' + str(num_cell) + '-rand_cell_ID.txt', draws)
-    spio.save_draw_tables([('%s/%s-up_log-pval' % (output_dir, num_cell), res["up"]),
-                           ('%s/%s-down_log-pval' % (output_dir, num_cell), res["down"]),
-                           ('%s/%s-cpm' % (output_dir, num_cell), res["cpm"])])
-
-    logger.info('Start modeling randomization distribution.')
-    cpm_mean = np.mean(res["cpm"], axis=0)
     gamma_fit = gamma_fit or os.environ.get("SPADE_GAMMA_FIT", "scipy")
     if gamma_fit not in ("scipy", "device"):
         logger.critical("Incorrect gamma fit method. Has to be either 'scipy' or 'device'")
         sys.exit(0)
-    fit = gamma_parameters if gamma_fit == "scipy" else (lambda t, w: gamma_parameters_device(t, w, local_rank))
-    logger.info('Process up-regulation.')
-    A, B, C = fit(res["up"], 'up')
-    logger.info('Process down-regulation.')
-    D, E, F = fit(res["down"], 'down')
+    finish_draws(engine, draws, num_cell, output_dir, gamma_fit)
+    engine.close()
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    if rank == 0:
+        logger.info('Job is done.')
+
+
+def _fit_block(up, down, gamma_fit, device):
+    """Gamma parameters of a block of gene columns: ``up`` / ``down`` CUDA tensors ``[S, g]``.
+    Returns ``[A, B, C, D, E, F]`` (up then down), each ``[g]``."""
+    if up.shape[1] == 0:
+        return [np.zeros(0)] * 6
+    if gamma_fit == "device":
+        return (list(gamma_parameters_device(up, 'up', device))
+                + list(gamma_parameters_device(down, 'down', device)))
+    return (list(gamma_parameters(up.cpu().numpy(), 'up'))
+            + list(gamma_parameters(down.cpu().numpy(), 'down')))
+
+
+def finish_draws(engine, draws, num_cell, output_dir, gamma_fit="scipy", timings=None):
+    """Everything after the draws (``DErand.py:190-302``): the tests of all draws in one batch,
+    the three sparse tables + the cell-ID listing, the gamma parameters and ``Cpm_mean``.
+
+    The dense tables stay on the GPU(s).  One rank: device tables ``[S, G]``.  Several ranks:
+    draws sharded round-robin, tables re-sharded by gene through the fused exchange
+    (``shard.run_gene_sharded``), so that every rank holds all draws of its genes - what the
+    column-compressed MAT tables, the per-gene gamma fit and ``Cpm_mean`` need.  Each rank builds
+    the payload of its gene columns on its GPU (``spade_csc_*``), and writes it into its slice
+    of the shared files; rank 0 writes the headers.  Only the stored entries cross PCIe (and the
+    dense ``up`` / ``down`` blocks when the unchanged scipy fit on the host is chosen).
+    ``timings``: optional dict that receives the wall seconds of the three phases."""
+    import time
+
+    import torch
+
+    t_start = time.perf_counter()
+
+    rank, local_rank, world = shard.world()
+    S, G = len(draws), engine.G
+    names = ("up", "down", "cpm")
+    files = {"up": '%s/%s-up_log-pval' % (output_dir, num_cell),
+             "down": '%s/%s-down_log-pval' % (output_dir, num_cell),
+             "cpm": '%s/%s-cpm' % (output_dir, num_cell)}
+    use_exchange = world > 1 and not engine.wide_genes and os.environ.get("SPADE_GATHER", "genes") == "genes"
+
+    if world > 1 and not use_exchange:
+        # tables gathered on the host of rank 0 (matrices with wide genes, or SPADE_GATHER=host|nccl)
+        res = shard.run_sharded(engine, draws, tables=names)
+        if rank != 0:
+            return
+        block = {n: torch.from_numpy(res[n]).cuda(local_rank) for n in names}
+        g0, g1, world_files = 0, G, 1
+    elif world == 1:
+        dev = torch.device("cuda", local_rank)
+        members, offsets = engine.pack_sets(draws)
+        block = {n: torch.empty((S, G), dtype=torch.float64, device=dev) for n in names}
+        engine.run_device(torch.from_numpy(members.astype(np.int32)).to(dev), offsets, block)
+        engine.check()
+        g0, g1, world_files = 0, G, 1
+    else:
+        exchange, _ = shard.run_gene_sharded(engine, draws, tables=names)
+        g0, g1 = exchange.gene_begin, exchange.gene_end
+        block = {n: exchange.tables[n][:S, :g1 - g0] for n in names}
+        world_files = world
+
+    torch.cuda.synchronize(local_rank)
+    t_tests = time.perf_counter()
+    if rank == 0:
+        spio.write_cell_ids(output_dir + '/' + str(num_cell) + '-rand_cell_ID.txt', draws)
+
+    # --- the three sparse tables: payload of this rank's gene columns, written into its slice
+    payload = {n: spio.device_payload(block[n], local_rank) for n in names}
+    if world_files == 1:
+        spio.save_payloads([(files[n], S, G) + payload[n] for n in names])
+    else:
+        import torch.distributed as dist
+        counts = [None] * world
+        dist.all_gather_object(counts, {n: (int(payload[n][0][-1]), payload[n][0]) for n in names})
+        for n in names:
+            first = int(sum(counts[r][n][0] for r in range(rank)))
+            total = int(sum(c[n][0] for c in counts))
+            layout = spio.SparseMatLayout(S, G, total)
+            if rank == 0:
+                jc, base = [np.zeros(1, dtype=np.int64)], 0
+                for r in range(world):
+                    jc.append(counts[r][n][1][1:].astype(np.int64) + base)
+                    base += counts[r][n][0]
+                fd = os.open(files[n], os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+                layout.write_frame(fd, np.concatenate(jc))
+                os.close(fd)
+            dist.barrier()                                   # the file exists and has its size
+            if payload[n][0][-1] > 0:
+                fd = os.open(files[n], os.O_RDWR)
+                layout.write_entries(fd, first, payload[n][1], payload[n][2])
+                os.close(fd)
+    del payload
+    t_files = time.perf_counter()
+
+    # --- gamma parameters and Cpm_mean of this rank's genes
+    if rank == 0:
+        logger.info('Start modeling randomization distribution.')
+    from .engine import column_mean
+    cpm_mean = column_mean(block["cpm"], local_rank)
+    if rank == 0:
+        logger.info('Process up-regulation.')
+        logger.info('Process down-regulation.')
+    parts = _fit_block(block["up"], block["down"], gamma_fit, local_rank) + [cpm_mean]
+    if world_files > 1:
+        import torch.distributed as dist
+        everyone = [None] * world if rank == 0 else None
+        dist.gather_object(parts, everyone, dst=0)
+        if rank != 0:
+            return
+        parts = [np.concatenate([everyone[r][i] for r in range(world)]) for i in range(7)]
+    A, B, C, D, E, F, cpm_mean = parts
+    if timings is not None:
+        timings.update(tests_s=t_tests - t_start, files_s=t_files - t_tests,
+                       gamma_fit_s=time.perf_counter() - t_files)
 
     # string concatenation as in DErand.py:295-302: output_dir must end with '/'
     np.save(output_dir + 'Up_dist_gamma-%s-A' % (num_cell), A)
@@ -180,8 +288,6 @@ def DE_random_cells(sub_df_file,
     np.save(output_dir + 'Down_dist_gamma-%s-B' % (num_cell), E)
     np.save(output_dir + 'Down_dist_gamma-%s-C' % (num_cell), F)
     np.save(output_dir + 'Cpm_mean-%s' % (num_cell), cpm_mean)
-
-    logger.info('Job is done.')
 
 
 if __name__ == '__main__':

@@ -34,6 +34,7 @@
 #include "common.cuh"
 #include "fused.cuh"
 #include "gamma_fit.cuh"
+#include "payload.cuh"
 #include "score.cuh"
 #include "stage.cuh"
 #include "tails.cuh"
@@ -1461,6 +1462,89 @@ int spade_score(int device, const double *rand, int rand_location, int64_t S, in
     }
     S_TRY(cudaDeviceSynchronize());
 #undef S_TRY
+    return SPADE_OK;
+}
+
+int spade_csc_count(int device, const double *table, int64_t S, int64_t G, int64_t ld, int32_t *jc)
+{
+    auto fail = [&](int code, const std::string &m) { g_create_error = m; return code; };
+    if (S < 0 || G < 0 || ld < G || !jc || (S > 0 && G > 0 && !table) || S > 0x7fffffff)
+        return fail(SPADE_ERR_ARG, "bad table / jc arguments");
+    jc[0] = 0;
+    if (G == 0) return SPADE_OK;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return fail(SPADE_ERR_CUDA, cudaGetErrorString(ce));
+    DevBuf<int32_t> cnt;
+    ce = cnt.reserve((size_t)G);
+    if (ce != cudaSuccess) return fail(SPADE_ERR_CUDA, cudaGetErrorString(ce));
+    k_csc_count<<<(unsigned)((G * 32 + 255) / 256), 256>>>(table, S, G, ld, cnt.p);
+    ce = cudaMemcpy(jc + 1, cnt.p, G * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) return fail(SPADE_ERR_CUDA, cudaGetErrorString(ce));
+    int64_t run = 0;
+    for (int64_t g = 1; g <= G; ++g) {
+        run += jc[g];
+        if (run > 0x7fffffff) return fail(SPADE_ERR_ARG, "more than 2^31 - 1 stored entries: too large for a MAT-v5 sparse array");
+        jc[g] = (int32_t)run;
+    }
+    return SPADE_OK;
+}
+
+int spade_csc_fill(int device, const double *table, int64_t S, int64_t G, int64_t ld, const int32_t *jc,
+                   int32_t *ir, double *pr, int out_location)
+{
+    auto fail = [&](int code, const std::string &m) { g_create_error = m; return code; };
+    if (S < 0 || G < 0 || ld < G || !jc || (S > 0 && G > 0 && !table))
+        return fail(SPADE_ERR_ARG, "bad table / jc arguments");
+    if (out_location != SPADE_HOST && out_location != SPADE_DEVICE) return fail(SPADE_ERR_ARG, "bad location");
+    const int64_t nnz = G > 0 ? jc[G] : 0;
+    if (nnz == 0) return SPADE_OK;
+    if (!ir || !pr) return fail(SPADE_ERR_ARG, "ir / pr is NULL");
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return fail(SPADE_ERR_CUDA, cudaGetErrorString(ce));
+#define P_TRY(expr)                                                                            \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return fail(SPADE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    DevBuf<int64_t> begin;
+    DevBuf<int32_t> dir;
+    DevBuf<double> dpr;
+    std::vector<int64_t> hb((size_t)G);
+    for (int64_t g = 0; g < G; ++g) hb[g] = jc[g] - jc[0];
+    P_TRY(begin.reserve((size_t)G));
+    P_TRY(cudaMemcpy(begin.p, hb.data(), G * sizeof(int64_t), cudaMemcpyHostToDevice));
+    int32_t *oir = ir;
+    double *opr = pr;
+    if (out_location == SPADE_HOST) {
+        P_TRY(dir.reserve((size_t)nnz));
+        P_TRY(dpr.reserve((size_t)nnz));
+        oir = dir.p;
+        opr = dpr.p;
+    }
+    k_csc_fill<<<(unsigned)((G * 32 + 255) / 256), 256>>>(table, S, G, ld, begin.p, oir, opr);
+    P_TRY(cudaGetLastError());
+    if (out_location == SPADE_HOST) {
+        P_TRY(cudaMemcpy(ir, dir.p, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        P_TRY(cudaMemcpy(pr, dpr.p, nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    P_TRY(cudaDeviceSynchronize());
+    return SPADE_OK;
+}
+
+int spade_column_mean(int device, const double *table, int64_t S, int64_t G, int64_t ld, double *mean)
+{
+    auto fail = [&](int code, const std::string &m) { g_create_error = m; return code; };
+    if (S < 0 || G < 0 || ld < G || (G > 0 && !mean) || (S > 0 && G > 0 && !table))
+        return fail(SPADE_ERR_ARG, "bad table / mean arguments");
+    if (G == 0) return SPADE_OK;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return fail(SPADE_ERR_CUDA, cudaGetErrorString(ce));
+    DevBuf<double> dm;
+    P_TRY(dm.reserve((size_t)G));
+    k_column_mean<<<(unsigned)((G * 32 + 255) / 256), 256>>>(table, S, G, ld, dm.p);
+    P_TRY(cudaGetLastError());
+    P_TRY(cudaMemcpy(mean, dm.p, G * sizeof(double), cudaMemcpyDeviceToHost));
+#undef P_TRY
     return SPADE_OK;
 }
 

@@ -421,12 +421,29 @@ def gamma_fit(table, sign=-1.0, device=0):
         S, G = t.shape
         ptr, loc = _ptr(t), _lib.SPADE_HOST
     else:
-        assert table.is_cuda and table.is_contiguous() and table.dim() == 2
+        assert table.is_cuda and table.dim() == 2 and table.stride(1) == 1
         S, G = table.shape
         ptr, loc = ctypes.c_void_p(table.data_ptr()), _lib.SPADE_DEVICE
+    ld = G if isinstance(table, np.ndarray) or S <= 1 else table.stride(0)
     A, B, C = np.zeros(G), np.zeros(G), np.zeros(G)
     status = np.zeros(G, dtype=np.int32)
-    rc = lib.spade_gamma_fit(int(device), ptr, loc, S, G, G, float(sign), _ptr(A), _ptr(B), _ptr(C), _ptr(status))
+    rc = lib.spade_gamma_fit(int(device), ptr, loc, S, G, ld, float(sign), _ptr(A), _ptr(B), _ptr(C), _ptr(status))
     if rc != _lib.SPADE_OK:
         raise SpadeError(f"spade_gamma_fit failed ({rc}): {lib.spade_last_error(None).decode()}")
     return A, B, C, status
+
+
+def column_mean(table, device=0):
+    """``spade_column_mean``: mean over the rows of every column of a CUDA float64 tensor
+    ``[S, G]`` (``Cpm_mean`` of ``DErand.py:252``).  Returns numpy ``[G]``."""
+    lib = _lib.load()
+    assert table.is_cuda and table.dim() == 2 and table.stride(1) == 1
+    S, G = table.shape
+    out = np.zeros(G, dtype=np.float64)
+    if G == 0:
+        return out
+    ld = table.stride(0) if S > 1 else max(G, 1)
+    rc = lib.spade_column_mean(int(device), ctypes.c_void_p(table.data_ptr()), S, G, ld, _ptr(out))
+    if rc != _lib.SPADE_OK:
+        raise SpadeError(f"spade_column_mean failed ({rc}): {lib.spade_last_error(None).decode()}")
+    return out

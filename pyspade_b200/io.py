@@ -7,6 +7,7 @@ variable name ``'matrix'`` (``DEobs.py:208-221``, ``DErand.py:230-248``); ``.npy
 the ``rand_cell_ID.txt`` listing.  Readers downstream: ``utils.load_data``
 (``utils.py:343-361``), ``local.py:81-110``, ``global.py:84-111``.
 """
+import os
 import struct
 
 import numpy as np
@@ -91,10 +92,66 @@ def save_vector(path, vec):
         fh.write(b"\x00" * pad)
 
 
-def save_draw_table(path, table):
-    """One DErand table: the sparse matrix ``csr_matrix(dense)`` (exact zeros dropped, nan /
-    -inf kept) under ``'matrix'`` - what ``DErand.py:230-248`` leaves on disk after the last
-    draw.  MAT sparse storage is column-compressed: row indices, column pointers, values."""
+class SparseMatLayout:
+    """Byte layout of a MAT-v5 file holding one sparse ``[S, G]`` float64 matrix named
+    ``'matrix'`` with ``nnz`` stored entries (column-compressed: ``ir`` row indices, ``jc``
+    column pointers, ``pr`` values) - what ``scipy.io.savemat(path, {'matrix': csr_matrix(x)})``
+    writes.  Knowing ``nnz`` fixes the offset of every array, so several writers (one per GPU
+    rank, each holding a block of gene columns) can fill one file with ``os.pwrite``."""
+
+    def __init__(self, S, G, nnz):
+        self.S, self.G, self.nnz = int(S), int(G), int(nnz)
+        self.nzmax = max(self.nnz, 1)            # scipy keeps one explicit slot for an empty matrix
+        self.prefix = _matrix_prefix(_MX_SPARSE, self.nzmax, (self.S, self.G))
+        ir_bytes, jc_bytes, pr_bytes = 4 * self.nzmax, 4 * (self.G + 1), 8 * self.nzmax
+        pad = lambda n: (-n) % 8                 # noqa: E731
+        at = 128 + 8 + len(self.prefix)
+        self.ir_tag, self.ir_off = at, at + 8
+        at = self.ir_off + ir_bytes + pad(ir_bytes)
+        self.jc_tag, self.jc_off = at, at + 8
+        at = self.jc_off + jc_bytes + pad(jc_bytes)
+        self.pr_tag, self.pr_off = at, at + 8
+        self.size = self.pr_off + pr_bytes + pad(pr_bytes)
+        self.element_bytes = self.size - 128 - 8
+        if self.element_bytes >= 1 << 32:
+            raise ValueError("table too large for a MAT-v5 element (same limit as scipy.io.savemat)")
+
+    def write_frame(self, fd, jc):
+        """Size the file and write everything except ``ir`` / ``pr``: headers, tags, ``jc``."""
+        os.ftruncate(fd, self.size)              # padding and the empty-matrix slot read as zeros
+        os.pwrite(fd, _mat_header() + struct.pack("<II", _MI_MATRIX, self.element_bytes) + self.prefix, 0)
+        os.pwrite(fd, _array_tag(_MI_INT32, 4 * self.nzmax), self.ir_tag)
+        os.pwrite(fd, _array_tag(_MI_INT32, 4 * (self.G + 1)), self.jc_tag)
+        os.pwrite(fd, np.ascontiguousarray(jc, dtype="<i4").tobytes(), self.jc_off)
+        os.pwrite(fd, _array_tag(_MI_DOUBLE, 8 * self.nzmax), self.pr_tag)
+
+    def write_entries(self, fd, first, ir, pr):
+        """Stored entries ``first .. first + len(ir)`` of the file (column-major order)."""
+        _pwrite_all(fd, memoryview(np.ascontiguousarray(ir, dtype="<i4")).cast("B"), self.ir_off + 4 * first)
+        _pwrite_all(fd, memoryview(np.ascontiguousarray(pr, dtype="<f8")).cast("B"), self.pr_off + 8 * first)
+
+
+def _pwrite_all(fd, view, offset):
+    done = 0
+    while done < len(view):
+        done += os.pwrite(fd, view[done:done + (1 << 30)], offset + done)
+
+
+def save_sparse_payload(path, S, G, jc, ir, pr):
+    """One DErand table from its column-compressed payload (``spade_csc_count`` /
+    ``spade_csc_fill`` on the GPU, or ``dense_payload`` on the host)."""
+    layout = SparseMatLayout(S, G, int(jc[-1]))
+    fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        layout.write_frame(fd, jc)
+        if layout.nnz:
+            layout.write_entries(fd, 0, ir, pr)
+    finally:
+        os.close(fd)
+
+
+def dense_payload(table):
+    """``(jc, ir, pr)`` of a dense host table: exact zeros dropped, nan / -inf kept."""
     table = np.asarray(table, dtype=np.float64)
     S, G = table.shape
     tt = np.ascontiguousarray(table.T)                      # [G, S]: one column of the table per row
@@ -103,26 +160,45 @@ def save_draw_table(path, table):
     np.cumsum(np.count_nonzero(mask, axis=1), out=jc[1:])
     ir = np.nonzero(mask)[1].astype("<i4")                  # row index of every stored value, column-major
     pr = tt[mask].astype("<f8", copy=False)
-    nnz = int(pr.shape[0])
-    if nnz == 0:
-        # scipy keeps one explicit slot for an empty sparse matrix (nzmax = 1)
-        ir, pr, nzmax = np.zeros(1, "<i4"), np.zeros(1, "<f8"), 1
+    return jc, ir, pr
+
+
+def device_payload(table, device=0):
+    """``(jc, ir, pr)`` numpy arrays of a CUDA float64 tensor ``[S, G]`` (any row stride), built
+    on the GPU: only the stored entries cross PCIe."""
+    import ctypes
+
+    from . import _lib
+    lib = _lib.load()
+    assert table.is_cuda and table.dim() == 2 and table.stride(1) == 1
+    S, G = table.shape
+    ld = table.stride(0) if S > 1 else max(G, 1)
+    tp = ctypes.c_void_p(table.data_ptr())
+    jc = np.zeros(G + 1, dtype=np.int32)
+
+    def ok(rc):
+        if rc != _lib.SPADE_OK:
+            raise RuntimeError("device payload: " + lib.spade_last_error(None).decode())
+
+    ok(lib.spade_csc_count(device, tp, S, G, ld, ctypes.c_void_p(jc.ctypes.data)))
+    nnz = int(jc[-1])
+    ir, pr = np.empty(nnz, dtype=np.int32), np.empty(nnz, dtype=np.float64)
+    ok(lib.spade_csc_fill(device, tp, S, G, ld, ctypes.c_void_p(jc.ctypes.data), ctypes.c_void_p(ir.ctypes.data),
+                          ctypes.c_void_p(pr.ctypes.data), _lib.SPADE_HOST))
+    return jc, ir, pr
+
+
+def save_draw_table(path, table):
+    """One DErand table: the sparse matrix ``csr_matrix(dense)`` (exact zeros dropped, nan /
+    -inf kept) under ``'matrix'`` - what ``DErand.py:230-248`` leaves on disk after the last
+    draw.  ``table``: host array, or a CUDA tensor (payload built on the GPU)."""
+    if isinstance(table, np.ndarray):
+        S, G = table.shape
+        jc, ir, pr = dense_payload(table)
     else:
-        nzmax = nnz
-    parts = [_matrix_prefix(_MX_SPARSE, nzmax, (S, G))]
-    for mdtype, arr in ((_MI_INT32, ir), (_MI_INT32, jc), (_MI_DOUBLE, pr)):
-        parts.append((_array_tag(mdtype, arr.nbytes), arr, b"\x00" * ((-arr.nbytes) % 8)))
-    total = len(parts[0]) + sum(len(t) + a.nbytes + len(pd_) for t, a, pd_ in parts[1:])
-    if total >= 1 << 32:
-        raise ValueError("table too large for a MAT-v5 element (same limit as scipy.io.savemat)")
-    with open(path, "wb") as fh:
-        fh.write(_mat_header())
-        fh.write(struct.pack("<II", _MI_MATRIX, total))
-        fh.write(parts[0])
-        for tag, arr, padding in parts[1:]:
-            fh.write(tag)
-            arr.tofile(fh)
-            fh.write(padding)
+        S, G = table.shape
+        jc, ir, pr = device_payload(table, table.device.index)
+    save_sparse_payload(path, S, G, jc, ir, pr)
 
 
 def save_draw_tables(items):
@@ -130,6 +206,13 @@ def save_draw_tables(items):
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=max(1, len(items))) as pool:
         list(pool.map(lambda pt: save_draw_table(*pt), items))
+
+
+def save_payloads(items):
+    """``[(path, S, G, jc, ir, pr), ...]`` written concurrently."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, len(items))) as pool:
+        list(pool.map(lambda it: save_sparse_payload(*it), items))
 
 
 def write_cell_ids(path, draws):

@@ -209,6 +209,7 @@ class GeneExchange:
             self.engine.run_raw_blocks(members, offsets, blocks, first_row, row_step, stream=main)
         if self.expanded is not None:
             main.wait_event(self.expanded)
+        self.flag.zero_()
         self._dist.all_reduce(self.flag)               # passes once every rank's kernel has finished
         landed = torch.cuda.Event()
         landed.record(main)
@@ -310,12 +311,13 @@ class SharedHostTables:
     path when the tables are wanted on the host (file writers, the e2e benchmark).
     ``touch=(first_row, row_step, count)``: the rows this rank will write, zero-filled by it
     before the tables are pinned (NUMA first touch; with ``device`` the thread is moved to the
-    CPUs next to that GPU while it does so)."""
+    CPUs next to that GPU while it does so).  ``touch_block=(first_col, last_col)``: the same for
+    a rank that will write those columns of every row."""
 
     DTYPE = {"up": np.float64, "down": np.float64, "fc": np.float64, "cpm": np.float64, "k": np.int32}
 
     def __init__(self, names, rows, cols, rank, world_size, pin=True, directory="/dev/shm", touch=None,
-                 device=None):
+                 device=None, touch_block=None):
         import torch.distributed as dist
 
         from . import _lib
@@ -350,6 +352,12 @@ class SharedHostTables:
             with _near_gpu(device):
                 for n in self.names:
                     self.rows_view(n, first_row, row_step, count)[:] = 0
+            dist.barrier()
+        if touch_block is not None:
+            # the same for a rank that will write a block of COLUMNS of every row (gene block)
+            with _near_gpu(device):
+                for n in self.names:
+                    self.arrays[n][:, touch_block[0]:touch_block[1]] = 0
             dist.barrier()
         if pin:
             for n in self.names:

@@ -21,7 +21,7 @@ def _ngpu():
         return 0
 
 
-def _torchrun(nproc, args, port, gather="host"):
+def _torchrun(nproc, args, port, gather="genes"):
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), SPADE_GATHER=gather)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "pyspade_b200"] + args
@@ -30,7 +30,8 @@ def _torchrun(nproc, args, port, gather="host"):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("bg,gather", [("complement", "host"), ("NonTarget", "host"), ("complement", "nccl")])
+@pytest.mark.parametrize("bg,gather", [("complement", "genes"), ("NonTarget", "genes"), ("complement", "host"),
+                                       ("NonTarget", "host"), ("complement", "nccl")])
 def test_two_rank_cli_matches_reference_files(tmp_path, cli_case, bg, gather):
     tpk, spk, dtx = _write_inputs(str(tmp_path), cli_case)
     od = str(tmp_path / "obs")
@@ -42,3 +43,12 @@ def test_two_rank_cli_matches_reference_files(tmp_path, cli_case, bg, gather):
     _torchrun(2, ["DErand", "-t", tpk, "-s", spk, "-d", dtx, "-o", od, "-b", bg, "-m", "20", "-i", "56",
                   "-a", "equal"], 29612, gather)
     _compare(_read_outputs(od), cli_case, f"DErand/{bg}/equal/")
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_gene_sharded_exchange_bit_identical():
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(_ngpu(), 4)}",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "tests", "_exchange_worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
