@@ -228,35 +228,50 @@ def finish_draws(engine, draws, num_cell, output_dir, gamma_fit="scipy", timings
 
     torch.cuda.synchronize(local_rank)
     t_tests = time.perf_counter()
-    if rank == 0:
-        spio.write_cell_ids(output_dir + '/' + str(num_cell) + '-rand_cell_ID.txt', draws)
 
-    # --- the three sparse tables: payload of this rank's gene columns, written into its slice
-    payload = {n: spio.device_payload(block[n], local_rank) for n in names}
+    # --- the three sparse tables: payload of this rank's gene columns, written into its slice.
+    # One thread per table (payload on the GPU, device->host copy, file write) so that the copy
+    # of one table overlaps the file write of another; the cell-ID listing goes alongside.
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=4)
+    jobs = []
+    if rank == 0:
+        jobs.append(pool.submit(spio.write_cell_ids, output_dir + '/' + str(num_cell) + '-rand_cell_ID.txt', draws))
     if world_files == 1:
-        spio.save_payloads([(files[n], S, G) + payload[n] for n in names])
+        def one_table(n):
+            jc, ir, pr = spio.device_payload(block[n], local_rank)
+            spio.save_sparse_payload(files[n], S, G, jc, ir, pr)
+        jobs += [pool.submit(one_table, n) for n in names]
+        for j in jobs:
+            j.result()
     else:
         import torch.distributed as dist
+        payload = {n: spio.device_payload(block[n], local_rank) for n in names}
         counts = [None] * world
         dist.all_gather_object(counts, {n: (int(payload[n][0][-1]), payload[n][0]) for n in names})
+        layouts = {}
         for n in names:
-            first = int(sum(counts[r][n][0] for r in range(rank)))
-            total = int(sum(c[n][0] for c in counts))
-            layout = spio.SparseMatLayout(S, G, total)
+            layouts[n] = spio.SparseMatLayout(S, G, int(sum(c[n][0] for c in counts)))
             if rank == 0:
                 jc, base = [np.zeros(1, dtype=np.int64)], 0
                 for r in range(world):
                     jc.append(counts[r][n][1][1:].astype(np.int64) + base)
                     base += counts[r][n][0]
                 fd = os.open(files[n], os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
-                layout.write_frame(fd, np.concatenate(jc))
+                layouts[n].write_frame(fd, np.concatenate(jc))
                 os.close(fd)
-            dist.barrier()                                   # the file exists and has its size
+        dist.barrier()                                       # the files exist and have their size
+
+        def one_slice(n):
             if payload[n][0][-1] > 0:
                 fd = os.open(files[n], os.O_RDWR)
-                layout.write_entries(fd, first, payload[n][1], payload[n][2])
+                layouts[n].write_entries(fd, int(sum(counts[r][n][0] for r in range(rank))), payload[n][1], payload[n][2])
                 os.close(fd)
-    del payload
+        jobs += [pool.submit(one_slice, n) for n in names]
+        for j in jobs:
+            j.result()
+        del payload
+    pool.shutdown()
     t_files = time.perf_counter()
 
     # --- gamma parameters and Cpm_mean of this rank's genes

@@ -25,6 +25,17 @@ constexpr int kMemberBlock = 32768;
 // Guaranteed relative accuracy of a fixed-point member mean of same-signed values; genes that
 // cannot meet it take the float64 side path (stage.cuh, wide.cuh).  Fold changes: twice this.
 constexpr double kWideRelBound = 0x1p-22;             // 2.4e-7
+// Two-choice accumulators (stage.cuh k_two_choice): every gene of a partition owns TWO
+// accumulators in different shared-memory bank pairs, A at index slot and B at index
+// Gp + alt_slot(slot); an entry carries the index of the one it adds into, chosen at staging time
+// so that the 16 entries a half-warp handles together never share a bank pair.  The test is
+// finished from A + B.  kTwoDummy spare accumulators (one per bank pair, never read) take the
+// holes of rows that could not be filled.
+constexpr int kTwoDummy = 16;
+__host__ __device__ __forceinline__ int alt_slot(int s)    // same 16-group, bank pair shifted by 1..15
+{
+    return (s & ~15) | ((s + 1 + ((s >> 4) % 15)) & 15);
+}
 constexpr int kSegAlign = 16;                         // entries: segments start on 128-byte lines
 #ifndef SPADE_DENSE_REGS
 #define SPADE_DENSE_REGS 1

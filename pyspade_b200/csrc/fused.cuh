@@ -48,6 +48,7 @@ struct FinCtx {
     double *up, *down, *fc, *cpm; // row 0 = first set of the launch; any may be null
     int32_t *k;
     int64_t ld;                   // row stride (elements)
+    int64_t k_ld;                 // row stride of k; 0 = ld
 };
 
 // One (gene, set) test from its member sum / member count (utils.py:203-215, 257-266), in two
@@ -106,7 +107,7 @@ __device__ __forceinline__ void fin_store(const FinCtx &f, int64_t row, int64_t 
         const double mean_bg = f.nc_mode ? it.mt.bgmean : fixed_mean(it.mt.rowsum - it.sumfx, it.mt.shift, invRest);
         f.fc[o] = fold_change(mean_set, mean_bg);
     }
-    if (f.k) f.k[o] = it.kk;
+    if (f.k) f.k[f.k_ld ? row * f.k_ld + g : o] = it.kk;
     if (f.up || f.down) {
         double lc, ls;
         if (it.how == 0) {
@@ -163,6 +164,8 @@ struct RunArgs {
     int64_t raw_row0, raw_row_step;
     int p0, p1;                   // gene partitions of this launch
     int Gp;
+    int two;                      // two-choice accumulators (common.cuh): a test is finished from A + B
+    int acc_len;                  // accumulators per warp: Gp, or 2 Gp + kTwoDummy
     int64_t C;
     FinCtx fin;
     int *err;
@@ -181,8 +184,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
 {
     extern __shared__ unsigned long long smem_acc[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long *acc = smem_acc + (size_t)warp * a.Gp;
-    uint2 *mbuf = reinterpret_cast<uint2 *>(smem_acc + (size_t)kWarpsPerCta * a.Gp) + warp * 32;
+    unsigned long long *acc = smem_acc + (size_t)warp * a.acc_len;
+    uint2 *mbuf = reinterpret_cast<uint2 *>(smem_acc + (size_t)kWarpsPerCta * a.acc_len) + warp * 32;
 
     const int64_t units = kSplit ? a.nblk : a.S;
     const int64_t t = blockIdx.x * (int64_t)kWarpsPerCta + warp;
@@ -206,8 +209,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     }
     const int64_t g0 = (int64_t)p * a.Gp;
     const int ng = (int)min((int64_t)a.Gp, a.fin.G - g0);
-    for (int j = lane; j < ng; j += 32) acc[j] = 0ull;
+    for (int j = lane; j < a.acc_len; j += 32) acc[j] = 0ull;
     __syncwarp();
+    // the accumulator word of gene j of the partition (count << 48 | sum)
+    auto word = [&](int j) -> unsigned long long {
+        return a.two ? acc[j] + acc[a.Gp + alt_slot(j)] : acc[j];
+    };
 
     const uint2 *__restrict__ seg = a.seg + (int64_t)p * a.C;
     const int32_t *__restrict__ mem = a.members + mbeg;
@@ -328,11 +335,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         while (b + 1 < a.ndst && p >= a.dst_pbegin[b + 1]) ++b;
         unsigned long long *dst = a.dst_base[b] + (a.raw_row0 + row * a.raw_row_step) * a.dst_ld[b] +
                                   (g0 - (int64_t)a.dst_pbegin[b] * a.Gp);
-        for (int j = lane; j < ng; j += 32) dst[j] = acc[j];
+        for (int j = lane; j < ng; j += 32) dst[j] = word(j);
     } else if (!kSplit && a.raw) {
         // raw form: the accumulator words leave as they are (8 bytes per test instead of 24-36);
         // whoever receives them finishes the tests with k_expand
-        for (int j = lane; j < ng; j += 32) a.raw[row * a.raw_ld + g0 + j] = acc[j];
+        for (int j = lane; j < ng; j += 32) a.raw[row * a.raw_ld + g0 + j] = word(j);
     } else if (!kSplit) {
         const double invN = 1.0 / (double)N;
         const double invRest = 1.0 / (double)((long long)a.C - N);
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
             for (int u = 0; u < kFinBatch; ++u) {
                 const int j = j0 + 32 * u;
                 if (j < ng) {
-                    const long long v = (long long)acc[j];
+                    const long long v = (long long)word(j);
                     const long long sumfx = (v << 16) >> 16;
                     const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
                     fin_load(a.fin, g0 + j, sumfx, cnt, N, it[u]);
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         }
     } else {
         for (int j = lane; j < ng; j += 32) {
-            const long long v = (long long)acc[j];
+            const long long v = (long long)word(j);
             if (v == 0) continue;
             const long long sumfx = (v << 16) >> 16;
             const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
@@ -472,7 +479,7 @@ k_expand(const FinCtx f, const unsigned long long *__restrict__ raw, int64_t raw
                                              : fixed_mean(mt.rowsum - sumfx, mt.shift, 1.0 / (double)((long long)f.M - N));
             __stcs(f.fc + o, fold_change(mean_set, mean_bg));
         }
-        if (f.k) f.k[o] = kk;
+        if (f.k) f.k[f.k_ld ? row * f.k_ld + col : o] = kk;
         if (f.up || f.down) {
             double lc, ls;
             if (kk == 0 || f.M == 0 || mt.n == 0 || N == 0) {

@@ -83,6 +83,8 @@ struct spade_engine {
     int bank_order = 1;                // lay segments out for conflict-free accumulator access
     int dense_blocks = 1;              // register-accumulated dense block per partition
     int sort_members = 1;              // walk every set in ascending cell order (L2 locality)
+    int two_choice = 0;                // two accumulators per gene, conflict-free rows (common.cuh)
+    int acc_len() const { return two_choice ? 2 * Gp + kTwoDummy : Gp; }
 
     DevBuf<int64_t> indptr;
     DevBuf<int32_t> indices;
@@ -122,6 +124,7 @@ struct spade_engine {
     DevBuf<int> gcnt;
     DevBuf<double> out_f64[4];         // host-output path: device tables of one batch
     DevBuf<int32_t> out_k;
+    DevBuf<int32_t> kbuf;              // counts of a ragged batch when the caller does not ask for k
     cudaStream_t work[2] = {nullptr, nullptr}, copy_stream = nullptr;
     cudaEvent_t ev_ready = nullptr;
     std::vector<cudaEvent_t> sync_events;
@@ -235,7 +238,12 @@ struct spade_engine {
         a.wide_flag = wide_flag.p;
         if (G > 0) k_gene_stage<<<(unsigned)G, kStageThreads, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
-        if (nnz > 0 && bank_order) {
+        if (nnz > 0 && two_choice) {
+            const int64_t nseg = (int64_t)P * C;
+            k_two_choice<<<(unsigned)((nseg + kTwoWarps - 1) / kTwoWarps), kTwoWarps * 32, 0, st>>>(
+                seg.p, cursor.p, nseg, C, Gp, dense_on.p, ent.p);
+            CUDA_TRY(cudaGetLastError());
+        } else if (nnz > 0 && bank_order) {
             const int64_t nseg = (int64_t)P * C;
             k_bank_order<<<(unsigned)((nseg + kOrderWarps - 1) / kOrderWarps), kOrderWarps * 32, 0, st>>>(
                 seg.p, nseg, C, dense_on.p, ent.p);
@@ -266,7 +274,7 @@ struct spade_engine {
 
         Gp = gp_request > 0 ? gp_request : kDefaultGenesPerPart;
         Gp = std::min<int64_t>(Gp, std::max<int64_t>(32, (G + 31) / 32 * 32));
-        Gp = std::max(32, std::min(Gp, 4096)) / 32 * 32;
+        Gp = std::max(32, std::min(Gp, two_choice ? 2048 : 4096)) / 32 * 32;
         P = (int)std::max<int64_t>(1, (G + Gp - 1) / Gp);
         if ((double)P * (double)C + 1 > 4.0e9) {
             set_error("partition index does not fit: (G / genes_per_part) * C must stay below 4e9");
@@ -343,14 +351,15 @@ struct spade_engine {
                 k_part_hist<<<(unsigned)G, kStageThreads, 0, st>>>(indptr.p, indices.p, C, Gp, dslot.p, count.p, d_err);
                 CUDA_TRY(cudaGetLastError());
             }
-            k_pad_counts<<<grid_for(np, 256), 256, 0, st>>>(count.p, (int64_t)np, C, dense_on.p, cursor.p);
+            k_pad_counts<<<grid_for(np, 256), 256, 0, st>>>(count.p, (int64_t)np, C, dense_on.p,
+                                                           two_choice ? 16u : 0u, cursor.p);
             CUDA_TRY(cudaGetLastError());
             size_t scan_bytes = 0;
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cursor.p, pptr.p, (int64_t)np, st));
             DevBuf<uint8_t> temp;
             CUDA_TRY(temp.reserve(scan_bytes));
             // padded total <= nnz + (dense head + 15) per segment: must fit the 32-bit entry index
-            if ((unsigned long long)nnz + (unsigned long long)(kSegAlign - 1 + (any_dense ? kDenseLanes : 0)) * np >
+            if ((unsigned long long)nnz + (unsigned long long)(kSegAlign - 1 + (two_choice ? 16 : 0) + (any_dense ? kDenseLanes : 0)) * np >
                 0xffff0000ull) {
                 set_error("matrix too large: padded entry count must stay below 2^32 - 65536");
                 return SPADE_ERR_ARG;
@@ -371,9 +380,9 @@ struct spade_engine {
         if (rc != SPADE_OK) return rc;
 
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kWarpsPerCta * (4096 + 32) * 8));
+                                      kWarpsPerCta * (4096 + kTwoDummy + 32) * 8));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kWarpsPerCta * (4096 + 32) * 8));
+                                      kWarpsPerCta * (4096 + kTwoDummy + 32) * 8));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         return stage_genes(st);
@@ -460,11 +469,29 @@ struct spade_engine {
         if (tasks <= 0) return SPADE_OK;
         const int64_t blocks = (tasks + kWarpsPerCta - 1) / kWarpsPerCta;
         if (blocks > 0x7fffffffll) { set_error("batch too large for one launch"); return SPADE_ERR_ARG; }
-        const size_t smem = (size_t)kWarpsPerCta * (Gp + 32) * sizeof(unsigned long long);   // accumulators + pair buffers
+        const size_t smem = (size_t)kWarpsPerCta * (acc_len() + 32) * sizeof(unsigned long long);   // accumulators + pair buffers
         int rc = span_begin(st, 0);
         if (rc != SPADE_OK) return rc;
         if (split) k_de_fused<true><<<(unsigned)blocks, kWarpsPerCta * 32, smem, st>>>(a);
         else k_de_fused<false><<<(unsigned)blocks, kWarpsPerCta * 32, smem, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        rc = span_end(st);
+        if (rc != SPADE_OK) return rc;
+        launches += 1;
+        return SPADE_OK;
+    }
+
+    // up / down of rows [0, Sb) x genes [g0, g1) from the counts the test kernel left in k
+    // (ragged batches, see k_tails_direct).  sizes: device N per row, or null -> offsets of set s0.
+    int launch_tails(cudaStream_t st, const int32_t *k, int64_t k_ld, const int64_t *sizes, int64_t s0, int64_t Sb,
+                     int64_t g0, int64_t g1, int64_t col0, double *up, double *down, int64_t ld)
+    {
+        if (Sb <= 0 || g1 <= g0 || (!up && !down)) return SPADE_OK;
+        int rc = span_begin(st, 2);
+        if (rc != SPADE_OK) return rc;
+        const dim3 grid((unsigned)((g1 - g0 + 255) / 256), (unsigned)std::min<int64_t>(Sb, 65535));
+        k_tails_direct<<<grid, 256, 0, st>>>(k, k_ld, meta.p, sizes, sizes ? nullptr : offsets.p + s0, (int)C, lf.p, up,
+                                             down, ld, Sb, g0, g1, col0);
         CUDA_TRY(cudaGetLastError());
         rc = span_end(st);
         if (rc != SPADE_OK) return rc;
@@ -534,6 +561,7 @@ struct spade_engine {
         blk_row.release(); blk_cnt.release(); blk_off.release(); gsum.release(); gcnt.release();
         for (int b = 0; b < 4; ++b) out_f64[b].release();
         out_k.release();
+        kbuf.release();
         h_tmeta.release();
         h_offsets.release();
         h_sizes.release();
@@ -580,6 +608,7 @@ int create_common(int device, int64_t G, int64_t C, const int64_t *indptr, const
     if (const char *gp = getenv("SPADE_GENES_PER_PART")) e->gp_request = atoi(gp);
     if (const char *bo = getenv("SPADE_BANK_ORDER")) e->bank_order = atoi(bo) != 0;
     if (const char *db = getenv("SPADE_DENSE_BLOCKS")) e->dense_blocks = atoi(db) != 0;
+    if (const char *tc = getenv("SPADE_TWO_CHOICE")) e->two_choice = atoi(tc) != 0;
     auto bail = [&](int code) {
         g_create_error = e->error;
         e->free_all();
@@ -880,6 +909,8 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
         a.s0 = s0;
         a.S = Sb;
         a.Gp = engine->Gp;
+        a.two = engine->two_choice;
+        a.acc_len = engine->acc_len();
         a.C = C;
         a.err = engine->d_err;
         a.raw = (raw && !blocks) ? raw + s0 * out_row_stride : nullptr;
@@ -918,6 +949,23 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             a.fin.fc = fc ? fc + s0 * out_row_stride : nullptr;
             a.fin.cpm = cpm ? cpm + s0 * out_row_stride : nullptr;
             a.fin.k = k ? k + s0 * out_row_stride : nullptr;
+        }
+
+        // Ragged batch (no tail table): the test kernel leaves the counts, k_tails_direct turns them
+        // into up / down afterwards at full occupancy.
+        const bool defer = !table && !raw && !split && (a.fin.up || a.fin.down);
+        double *t_up = a.fin.up, *t_down = a.fin.down;
+        const int32_t *t_k = a.fin.k;
+        int64_t t_kld = a.fin.ld;
+        if (defer) {
+            if (!a.fin.k) {
+                CUDA_TRY(engine->kbuf.reserve(Sb * G));
+                a.fin.k = engine->kbuf.p;
+                a.fin.k_ld = G;
+                t_k = engine->kbuf.p;
+                t_kld = G;
+            }
+            a.fin.up = a.fin.down = nullptr;
         }
 
         if (split) {
@@ -979,6 +1027,10 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             a.p1 = P;
             int rc = engine->launch_fused(a, false, st);
             if (rc != SPADE_OK) return rc;
+            if (defer) {
+                rc = engine->launch_tails(st, t_k, t_kld, nullptr, s0, Sb, 0, G, 0, t_up, t_down, a.fin.ld);
+                if (rc != SPADE_OK) return rc;
+            }
             if (!raw) {
                 rc = engine->fix_wide(st, 0, d_members, s0, Sb, 0, G, a.fin.fc, a.fin.cpm, a.fin.ld);
                 if (rc != SPADE_OK) return rc;
@@ -997,6 +1049,11 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
                 a.p1 = std::min(P, p0 + pg);
                 int rc = engine->launch_fused(a, false, ws);
                 if (rc != SPADE_OK) return rc;
+                if (defer) {
+                    rc = engine->launch_tails(ws, t_k, t_kld, nullptr, s0, Sb, (int64_t)a.p0 * engine->Gp,
+                                              std::min<int64_t>(G, (int64_t)a.p1 * engine->Gp), 0, t_up, t_down, a.fin.ld);
+                    if (rc != SPADE_OK) return rc;
+                }
                 rc = engine->fix_wide(ws, (int)(gi & 1), d_members, s0, Sb, (int64_t)a.p0 * engine->Gp,
                                       std::min<int64_t>(G, (int64_t)a.p1 * engine->Gp), a.fin.fc, a.fin.cpm, a.fin.ld);
                 if (rc != SPADE_OK) return rc;
@@ -1138,6 +1195,21 @@ int spade_expand_block(spade_engine *engine, const uint64_t *raw, int64_t rows, 
     f.lf = engine->lf.p;
     f.up = up; f.down = down; f.fc = fc; f.cpm = cpm; f.k = k;
     f.ld = out_row_stride;
+    f.k_ld = 0;
+    // ragged rows (no tail table): leave the counts, evaluate the tails at full occupancy afterwards
+    const bool defer = !table && (up || down);
+    const int32_t *t_k = k;
+    int64_t t_kld = out_row_stride;
+    if (defer) {
+        if (!k) {
+            CUDA_TRY(engine->kbuf.reserve((size_t)rows * (size_t)gene_count));
+            f.k = engine->kbuf.p;
+            f.k_ld = gene_count;
+            t_k = engine->kbuf.p;
+            t_kld = gene_count;
+        }
+        f.up = f.down = nullptr;
+    }
     int rc = engine->span_begin(st, 2);
     if (rc != SPADE_OK) return rc;
     const int64_t rows_per_launch = (int64_t)65535 * kExpandRows;        // gridDim.y limit
@@ -1157,6 +1229,11 @@ int spade_expand_block(spade_engine *engine, const uint64_t *raw, int64_t rows, 
     rc = engine->span_end(st);
     if (rc != SPADE_OK) return rc;
     engine->launches += 1;
+    if (defer) {
+        rc = engine->launch_tails(st, t_k, t_kld, engine->sizes.p, 0, rows, gene_begin, gene_begin + gene_count,
+                                  gene_begin, up, down, out_row_stride);
+        if (rc != SPADE_OK) return rc;
+    }
     return SPADE_OK;
 }
 

@@ -61,13 +61,14 @@ k_part_hist(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indi
 // head of every segment: kDenseLanes words, word l = the partition's l-th densest gene in this
 // cell (zero = not expressed), then the packed entries of the other genes.
 // padded[i] = (dense head + count[i]) rounded up to 16.
+// `spare` extra entries per non-empty segment (the two-choice layout may need one more row).
 __global__ void k_pad_counts(const uint32_t *__restrict__ count, int64_t n, int64_t C,
-                             const uint8_t *__restrict__ dense_on, uint32_t *__restrict__ padded)
+                             const uint8_t *__restrict__ dense_on, uint32_t spare, uint32_t *__restrict__ padded)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t head = dense_on[i / C] ? kDenseLanes : 0;
-        padded[i] = (head + count[i] + (kSegAlign - 1)) & ~(uint32_t)(kSegAlign - 1);
+        padded[i] = ((head + count[i] + (kSegAlign - 1)) & ~(uint32_t)(kSegAlign - 1)) + (count[i] ? spare : 0);
     }
 }
 
@@ -296,43 +297,37 @@ __global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
 constexpr int kOrderChunk = 512;
 constexpr int kOrderWarps = 8;
 
-__global__ void __launch_bounds__(kOrderWarps * 32)
-k_bank_order(const uint2 *__restrict__ segs, int64_t nseg, int64_t C, const uint8_t *__restrict__ dense_on,
-             unsigned long long *__restrict__ ent)
+// entries [beg, end) of one segment, chunk by chunk; `buf` / `bins`: this warp's scratch
+__device__ void bank_order_segment(unsigned long long *__restrict__ ent, uint32_t beg, uint32_t end,
+                                   unsigned long long *buf /*kOrderChunk*/, int *bins /*16*/, int lane)
 {
-    __shared__ unsigned long long buf[kOrderWarps][kOrderChunk];
-    __shared__ int bins[kOrderWarps][16];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t seg = blockIdx.x * (int64_t)kOrderWarps + warp;
-    if (seg >= nseg) return;
-    const uint32_t beg = segs[seg].x + (dense_on[seg / C] ? kDenseLanes : 0), end = segs[seg].y;
     for (uint32_t c0 = beg; c0 < end; c0 += kOrderChunk) {
         const int m = (int)min((uint32_t)kOrderChunk, end - c0);
         if (m <= 16) break;                                  // a single row: nothing to gain
         const int rows = (m + 15) >> 4;
         const int r = m - 16 * (rows - 1);                   // entries of the last row
-        if (lane < 16) bins[warp][lane] = 0;
+        if (lane < 16) bins[lane] = 0;
         __syncwarp();
         for (int i = lane; i < m; i += 32) {
             const unsigned long long e = ent[c0 + i];
-            buf[warp][i] = e;
-            atomicAdd(&bins[warp][(int)(e >> kFieldBits) & 15], 1);
+            buf[i] = e;
+            atomicAdd(&bins[(int)(e >> kFieldBits) & 15], 1);
         }
         __syncwarp();
         {   // exclusive scan of the 16 bins
-            int v = lane < 16 ? bins[warp][lane] : 0, inc = v;
+            int v = lane < 16 ? bins[lane] : 0, inc = v;
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
             __syncwarp();
-            if (lane < 16) bins[warp][lane] = inc - v;
+            if (lane < 16) bins[lane] = inc - v;
         }
         __syncwarp();
         for (int i = lane; i < m; i += 32) {
-            const unsigned long long e = buf[warp][i];
-            const int j = atomicAdd(&bins[warp][(int)(e >> kFieldBits) & 15], 1);   // rank in bank order
+            const unsigned long long e = buf[i];
+            const int j = atomicAdd(&bins[(int)(e >> kFieldBits) & 15], 1);   // rank in bank order
             int row, col;
             if (j < r * rows) {
                 col = j / rows;
@@ -346,6 +341,116 @@ k_bank_order(const uint2 *__restrict__ segs, int64_t nseg, int64_t C, const uint
         }
         __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(kOrderWarps * 32)
+k_bank_order(const uint2 *__restrict__ segs, int64_t nseg, int64_t C, const uint8_t *__restrict__ dense_on,
+             unsigned long long *__restrict__ ent)
+{
+    __shared__ unsigned long long buf[kOrderWarps][kOrderChunk];
+    __shared__ int bins[kOrderWarps][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t seg = blockIdx.x * (int64_t)kOrderWarps + warp;
+    if (seg >= nseg) return;
+    const uint32_t beg = segs[seg].x + (dense_on[seg / C] ? kDenseLanes : 0), end = segs[seg].y;
+    bank_order_segment(ent, beg, end, buf[warp], bins[warp], lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-choice layout (see common.cuh): per segment, pick for every entry accumulator A or B so
+// that no bank pair is asked for more than ceil(n / 16) times (greedy on the emptier of the two
+// banks, then single and double moves out of overfull banks), and store the entries as rows of
+// 16 with COLUMN = BANK PAIR: lane j of a half-warp always touches bank pair j, so the
+// read-modify-write of a row is one conflict-free wavefront.  Cell (row r, bank b) holds the
+// r-th entry of bank b or a hole (zero add into the spare accumulator of bank b).  A segment
+// gets ceil(n / 16) rows, one more when the assignment needs it (the layout reserves it); in the
+// rare case that even that is not enough, or for segments above kOrderChunk entries, the
+// conflict-tolerant order above is used instead.  The kernel rewrites seg[].y (end of the rows).
+// ------------------------------------------------------------------------------------------
+constexpr int kTwoWarps = 6;        // warps per CTA of k_two_choice (7.7 KB of scratch per warp)
+
+__global__ void __launch_bounds__(kTwoWarps * 32)
+k_two_choice(uint2 *__restrict__ segs, const uint32_t *__restrict__ cursor, int64_t nseg, int64_t C, int Gp,
+             const uint8_t *__restrict__ dense_on, unsigned long long *__restrict__ ent)
+{
+    __shared__ unsigned long long buf[kTwoWarps][kOrderChunk];
+    __shared__ int bins[kTwoWarps][16];
+    __shared__ uint8_t bank[kTwoWarps][kOrderChunk];       // chosen bank pair of every entry
+    __shared__ uint8_t other[kTwoWarps][kOrderChunk];      // its alternative
+    __shared__ uint16_t rank_in_bank[kTwoWarps][kOrderChunk];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t seg = blockIdx.x * (int64_t)kTwoWarps + warp;
+    if (seg >= nseg) return;
+    const uint32_t beg = segs[seg].x + (dense_on[seg / C] ? kDenseLanes : 0);
+    const uint32_t end = cursor[seg];                        // one past the last scattered entry
+    const int n = (int)(end - beg);
+    if (n == 0) return;
+    if (n > kOrderChunk) {                                   // very dense cell: conflict-tolerant order, A only
+        bank_order_segment(ent, beg, end, buf[warp], bins[warp], lane);
+        if (lane == 0) segs[seg].y = end;
+        return;
+    }
+    unsigned long long *b = buf[warp];
+    uint8_t *bk = bank[warp], *ot = other[warp];
+    int *load = bins[warp];
+    for (int i = lane; i < n; i += 32) b[i] = ent[beg + i];
+    if (lane < 16) load[lane] = 0;
+    __syncwarp();
+    const int L = (n + 15) >> 4;
+    int rows = 0;
+    if (lane == 0) {
+        for (int i = 0; i < n; ++i) {                        // greedy: the emptier of the two banks
+            const int s = (int)(b[i] >> kFieldBits);
+            const int a = s & 15, o = alt_slot(s) & 15;
+            if (load[a] <= load[o]) { bk[i] = a; ot[i] = o; ++load[a]; }
+            else { bk[i] = o; ot[i] = a; ++load[o]; }
+        }
+        for (int pass = 0; pass < 4; ++pass) {               // moves out of banks above L
+            bool over = false;
+            for (int i = 0; i < n; ++i) {
+                const int cur = bk[i];
+                if (load[cur] <= L) continue;
+                const int o = ot[i];
+                if (load[o] < L) {
+                    bk[i] = o; ot[i] = cur; --load[cur]; ++load[o];
+                    continue;
+                }
+                bool moved = false;                          // make room in o by moving one of its entries on
+                for (int j = 0; j < n && !moved; ++j) {
+                    if (bk[j] != o || load[ot[j]] >= L) continue;
+                    const int o2 = ot[j];
+                    bk[j] = o2; ot[j] = o; ++load[o2];       // j: o -> o2, i: cur -> o (load[o] unchanged)
+                    bk[i] = o; ot[i] = cur; --load[cur];
+                    moved = true;
+                }
+                over |= !moved;
+            }
+            if (!over) break;
+        }
+        int mx = 0;
+        for (int k = 0; k < 16; ++k) { mx = max(mx, load[k]); load[k] = 0; }
+        for (int i = 0; i < n; ++i) rank_in_bank[warp][i] = (uint16_t)load[bk[i]]++;
+        rows = mx;
+    }
+    rows = __shfl_sync(0xffffffffu, rows, 0);
+    __syncwarp();
+    if (rows > L + 1) {                                      // does not fit the reserved rows: keep A, old order
+        bank_order_segment(ent, beg, end, buf[warp], bins[warp], lane);
+        if (lane == 0) segs[seg].y = end;
+        return;
+    }
+    // holes first, then the entries (index rewritten to the chosen accumulator)
+    for (int i = lane; i < rows * 16; i += 32)
+        ent[beg + i] = (unsigned long long)(2 * Gp + (i & 15)) << kFieldBits;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const unsigned long long e = b[i];
+        const int s = (int)(e >> kFieldBits);
+        const int idx = (bk[i] == (s & 15)) ? s : Gp + alt_slot(s);
+        ent[beg + rank_in_bank[warp][i] * 16 + bk[i]] =
+            ((unsigned long long)idx << kFieldBits) | (e & ((1ull << kFieldBits) - 1));
+    }
+    if (lane == 0) segs[seg].y = beg + rows * 16;
 }
 
 }  // namespace spade

@@ -93,6 +93,32 @@ k_tail_table(const TabMeta *__restrict__ tmeta, const GeneMeta *__restrict__ met
     }
 }
 
+// Direct tails of finished counts, for batches whose sets differ in size (DEobs: no tail table).
+// The fused kernel leaves k[row][gene]; here one thread per test evaluates hyper_tails at full
+// occupancy (the fused kernel keeps 8 KB of shared memory per warp and 24 warps per SM, which
+// starves this FP64-bound step).  Rows [0, S), genes [g0, g1); sizes[row] = N of the row's set
+// (or offsets[row + 1] - offsets[row] when sizes is null).
+__global__ void __launch_bounds__(256)
+k_tails_direct(const int32_t *__restrict__ k, int64_t k_ld, const GeneMeta *__restrict__ meta,
+               const int64_t *__restrict__ sizes, const int64_t *__restrict__ offsets, int M,
+               const double *__restrict__ lf, double *__restrict__ up, double *__restrict__ down, int64_t ld,
+               int64_t S, int64_t g0, int64_t g1, int64_t col0)
+{
+    const int64_t g = g0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= g1) return;
+    const int n = meta[g].n;
+    const int64_t col = g - col0;                          // column of gene g in k / up / down
+    for (int64_t row = blockIdx.y; row < S; row += gridDim.y) {
+        const long long N = sizes ? sizes[row] : offsets[row + 1] - offsets[row];
+        const int kk = k[row * k_ld + col];
+        double lc, ls;
+        if (kk == 0 || M == 0 || n == 0 || N == 0) lc = ls = __longlong_as_double(0x7ff8000000000000ll);
+        else hyper_tails(kk, M, n, (int)N, lf, lc, ls);
+        if (up) up[row * ld + col] = lc;
+        if (down) down[row * ld + col] = ls;
+    }
+}
+
 __global__ void k_hyper_probe(const int64_t *__restrict__ k, const int64_t *__restrict__ M,
                               const int64_t *__restrict__ n, const int64_t *__restrict__ N,
                               int64_t count, const double *__restrict__ lf,

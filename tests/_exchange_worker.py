@@ -45,7 +45,8 @@ def main():
             assert np.array_equal(ex.k[:len(sets), :g1 - g0].cpu().numpy(), want["k"][order][:, g0:g1]), (name, rank)
         ex.close()
     # a bad member list on ONE rank makes every rank raise together
-    bad = [np.array([1, 2, 3]), np.array([4, 5, C + 7] if rank == 0 else [4, 5, 6])]
+    # (round-robin: set 0 is tested by rank 0, whose copy of it holds a cell index out of range)
+    bad = [np.array([1, 2, C + 7] if rank == 0 else [1, 2, 3]), np.array([4, 5, 6])]
     try:
         shard.run_gene_sharded(eng, bad, tables=("up",))
         raise SystemExit("expected an error")

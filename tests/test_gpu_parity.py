@@ -326,14 +326,21 @@ def test_layout_switches_do_not_change_results(monkeypatch):
     sets = synth.deobs_sets(C, 9, lo=5, hi=1200) + synth.derand_draws(C, 77, 5)
     nc = np.arange(1, C, 13)
     res = {}
-    for dense, order in ((1, 1), (0, 1), (1, 0), (0, 0)):
+    for dense, order in ((1, 1), (0, 1), (1, 0), (0, 0), (1, "two"), (0, "two")):
         monkeypatch.setenv("SPADE_DENSE_BLOCKS", str(dense))
-        monkeypatch.setenv("SPADE_BANK_ORDER", str(order))
+        monkeypatch.setenv("SPADE_BANK_ORDER", "1" if order == "two" else str(order))
+        monkeypatch.setenv("SPADE_TWO_CHOICE", "1" if order == "two" else "0")   # two accumulators per gene
         with Engine.from_counts(counts) as eng:
             a = eng.run(sets, want_k=True)
             eng.set_background(nc)
             b = eng.run(sets, want_k=True)
+            if order == "two":                              # re-staging and other partition widths
+                eng.set_background(None)
+                _tables_equal(a, eng.run(sets, want_k=True))
+                eng.set_option("genes_per_part", 96)
+                _tables_equal(a, eng.run(sets, want_k=True))
         res[(dense, order)] = (a, b)
+    monkeypatch.setenv("SPADE_TWO_CHOICE", "0")
     with Engine.from_counts(counts) as eng:
         eng.set_option("sort_members", 0)               # caller's member order
         res["unsorted"] = (eng.run(sets, want_k=True), None)
