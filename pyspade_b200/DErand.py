@@ -99,19 +99,12 @@ def DE_random_cells(sub_df_file,
         logger.critical("Incorrect randomization method. Has to be either 'equal' or 'sgrna'")
         sys.exit(0)
 
-    logger.info('Reading transcriptome file.')
-    trans_df = spio.read_frame(sub_df_file)
-    columns = trans_df.columns
-    counts = spio.frame_to_csr(trans_df)
-    del trans_df
-    G = counts.shape[0]
-    engine = Engine.from_counts(counts, device=local_rank)
-    del counts
-    logger.info('Finished transcriptome normalization.')
-
+    # The sgRNA table comes first: it fixes the population, the weights and the background
+    # cells, i.e. everything the draws depend on.  The draws - the reference's sequential legacy
+    # RNG stream, the largest host cost of a bin - then run in a second thread while this thread
+    # reads and stages the transcriptome (numpy releases the GIL inside the shuffles).
     sgrna_df_adj_bool = (spio.read_frame(sgrna_df) > 0)
     [g, c] = sgrna_df_adj_bool.shape
-    assert np.sum(columns == sgrna_df_adj_bool.columns) == c
     if RAND_M == 'sgrna':
         per_cell = np.asarray(sgrna_df_adj_bool.sum(axis=0).values, dtype=np.int64)
         total_choose_num = per_cell.sum()
@@ -121,6 +114,7 @@ def DE_random_cells(sub_df_file,
 
     population = np.arange(c)
     weights = sgrna_weight_list if RAND_M == 'sgrna' else None
+    NC_idx = None
     if background_cells != 'complement':
         sgrna_dict = read_sgrna_dict(sgrnas_file)
         if background_cells not in sgrna_dict:
@@ -136,23 +130,48 @@ def DE_random_cells(sub_df_file,
             logger.critical('No cell as background. Please consider other background set. Job cancels.')
             sys.exit(0)
         logger.info(str(len(NC_idx)) + ' cells as background for differential expression analysis.')
-        engine.set_background(NC_idx)
         population = np.setxor1d(np.arange(c), NC_idx)              # DErand.py:129-133
         if weights is not None:
             weights = sgrna_weight_list[list(population)]
             weights /= weights.sum()
+    sgrna_columns = sgrna_df_adj_bool.columns
     del sgrna_df_adj_bool
 
     # The draws: the reference's RNG calls, in the reference's order, before any sharding.
     logger.info('Start randomization Calculation.')
-    draws = []
-    for i in np.arange(iteration):
-        if i % 25 == 0:
-            logger.info('Finished ' + str(i) + ' iterations.')
-        if weights is not None:
-            draws.append(np.random.choice(population, size=num_cell, replace=False, p=weights))
-        else:
-            draws.append(np.random.choice(population, size=num_cell, replace=False))
+    draws, failure = [], []
+
+    def draw_all():
+        try:
+            for i in np.arange(iteration):
+                if i % 25 == 0:
+                    logger.info('Finished ' + str(i) + ' iterations.')
+                if weights is not None:
+                    draws.append(np.random.choice(population, size=num_cell, replace=False, p=weights))
+                else:
+                    draws.append(np.random.choice(population, size=num_cell, replace=False))
+        except BaseException as exc:                                 # noqa: BLE001 - re-raised by the main thread
+            failure.append(exc)
+
+    import threading
+    drawer = threading.Thread(target=draw_all, name="derand-draws")
+    drawer.start()
+    try:
+        logger.info('Reading transcriptome file.')
+        trans_df = spio.read_frame(sub_df_file)
+        columns = trans_df.columns
+        assert len(columns) == c and np.sum(columns == sgrna_columns) == c
+        counts = spio.frame_to_csr(trans_df)
+        del trans_df
+        engine = Engine.from_counts(counts, device=local_rank)
+        del counts
+        logger.info('Finished transcriptome normalization.')
+        if NC_idx is not None:
+            engine.set_background(NC_idx)
+    finally:
+        drawer.join()
+    if failure:
+        raise failure[0]
 
     gamma_fit = gamma_fit or os.environ.get("SPADE_GAMMA_FIT", "scipy")
     if gamma_fit not in ("scipy", "device"):

@@ -145,6 +145,8 @@ struct RunArgs {
     const int64_t *offsets;       // device copy of the caller's offsets
     int64_t s0;                   // first set of this launch
     int64_t S;                    // sets of this launch
+    const int32_t *order;         // ragged batches: sets (relative to s0) by decreasing size, so that the
+                                  // long tasks of a partition start first; null = as given
     // split mode (some set larger than the member block): work units are member blocks
     const int32_t *blk_row;       // set index relative to s0
     const int64_t *blk_off;       // absolute offset into members
@@ -202,9 +204,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         mbeg = a.blk_off[u];
         cntm = a.blk_cnt[u];
     } else {
-        row = u;
-        mbeg = a.offsets[a.s0 + u];
-        N = a.offsets[a.s0 + u + 1] - mbeg;
+        row = a.order ? a.order[u] : u;
+        mbeg = a.offsets[a.s0 + row];
+        N = a.offsets[a.s0 + row + 1] - mbeg;
         cntm = (int)N;
     }
     const int64_t g0 = (int64_t)p * a.Gp;

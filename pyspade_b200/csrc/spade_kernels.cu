@@ -132,6 +132,8 @@ struct spade_engine {
     int64_t tab_epoch = -1, bg_epoch = 0;
     PinnedBuf<TabMeta> h_tmeta;
     PinnedBuf<int64_t> h_offsets, h_sizes;
+    PinnedBuf<int32_t> h_order;
+    DevBuf<int32_t> order;             // ragged batches: sets by decreasing size
     DevBuf<int64_t> sizes;             // spade_expand's own upload buffers (it may run on another stream)
 
     std::vector<TimedSpan> spans;
@@ -565,6 +567,8 @@ struct spade_engine {
         h_tmeta.release();
         h_offsets.release();
         h_sizes.release();
+        h_order.release();
+        order.release();
         sizes.release();
         for (int i = 0; i < 2; ++i) {
             if (work[i]) cudaStreamDestroy(work[i]);
@@ -949,6 +953,20 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             a.fin.fc = fc ? fc + s0 * out_row_stride : nullptr;
             a.fin.cpm = cpm ? cpm + s0 * out_row_stride : nullptr;
             a.fin.k = k ? k + s0 * out_row_stride : nullptr;
+        }
+
+        // Ragged batch: longest sets first (the cost of a warp's task is proportional to its set size;
+        // in the given order a few large regions scheduled late leave most of the GPU idle at the end)
+        if (!uniform && !split && Sb > 1) {
+            CUDA_TRY(engine->h_order.reserve((size_t)Sb));
+            CUDA_TRY(engine->order.reserve((size_t)Sb));
+            int32_t *o = engine->h_order.p;
+            for (int64_t i = 0; i < Sb; ++i) o[i] = (int32_t)i;
+            std::stable_sort(o, o + Sb, [&](int32_t x, int32_t y) {
+                return offsets[s0 + x + 1] - offsets[s0 + x] > offsets[s0 + y + 1] - offsets[s0 + y];
+            });
+            CUDA_TRY(engine->h_order.upload(engine->order.p, (size_t)Sb, st));
+            a.order = engine->order.p;
         }
 
         // Ragged batch (no tail table): the test kernel leaves the counts, k_tails_direct turns them

@@ -6,7 +6,7 @@
 
 namespace spade {
 
-constexpr double kTailEps = 1e-18;
+constexpr double kTailEps = 1e-15;      // terms below this fraction of the running sum end a tail series
 
 __device__ __forceinline__ double ln_choose(const double *__restrict__ lf, int a, int b)
 {

@@ -288,3 +288,74 @@ def test_gene_blocks_tile_all_genes_on_partition_boundaries():
             assert all(a % Gp == 0 for a, b in blocks if b > a)
             widths = [b - a for a, b in blocks]
             assert max(widths) - min(widths) <= Gp                 # as even as whole partitions allow
+
+def _slices_worker(rank, world, port, path, q):
+    """One 'rank' of the gene-sharded DErand finish on the CPU: it owns a block of gene columns of
+    the table, builds their payload, learns the others' entry counts, and fills its slice of the
+    one shared file (what ``DErand.finish_draws`` does with GPU-built payloads)."""
+    import torch.distributed as dist
+    from pyspade_b200 import io as spio
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)                       # the same table on every rank
+        S, G = 40, 23
+        t = rng.normal(size=(S, G))
+        t[rng.random((S, G)) < 0.5] = 0.0
+        t[rng.random((S, G)) < 0.05] = np.nan
+        t[rng.random((S, G)) < 0.05] = -np.inf
+        blocks = shard.gene_blocks(G, 8, world)              # partitions of 8 genes
+        g0, g1 = blocks[rank]
+        jc, ir, pr = spio.dense_payload(t[:, g0:g1])
+        counts = [None] * world
+        dist.all_gather_object(counts, (int(jc[-1]), jc))
+        layout = spio.SparseMatLayout(S, G, sum(c[0] for c in counts))
+        if rank == 0:
+            full, base = [np.zeros(1, dtype=np.int64)], 0
+            for n, j in counts:
+                full.append(j[1:].astype(np.int64) + base)
+                base += n
+            fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+            layout.write_frame(fd, np.concatenate(full))
+            os.close(fd)
+        dist.barrier()
+        if jc[-1] > 0:
+            fd = os.open(path, os.O_RDWR)
+            layout.write_entries(fd, sum(c[0] for c in counts[:rank]), ir, pr)
+            os.close(fd)
+        dist.barrier()
+        # one rank failing makes every rank raise
+        try:
+            shard._raise_together(ValueError("boom") if rank == 1 else None, rank)
+            q.put("no error")
+        except ValueError:
+            q.put("ValueError" if rank == 1 else "wrong")
+        except RuntimeError:
+            q.put("RuntimeError" if rank != 1 else "wrong")
+        if rank == 0:
+            q.put(t)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_file_slices_and_joint_failure_world_size_2_gloo(tmp_path):
+    import scipy.sparse as sp
+    import torch.multiprocessing as mp
+    from scipy import io as sio
+    world, path = 2, str(tmp_path / "20-up_log-pval")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slices_worker, args=(r, world, port, path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world + 1)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(g for g in got if isinstance(g, str)) == ["RuntimeError", "ValueError"]
+    t = next(g for g in got if not isinstance(g, str))
+    a = sio.loadmat(path)["matrix"].tocsc()
+    b = sp.csc_matrix(sp.csr_matrix(t))
+    assert a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+    assert np.array_equal(a.data.view(np.int64), b.data.view(np.int64))
