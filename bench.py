@@ -303,7 +303,7 @@ def measure_config(st, name, workload, sets, tables, reps, peak, background=None
             "tables": list(tables), "value": S * G / (ms * 1e-3), "unit": UNIT, "ms_per_pass": ms,
             "kernel_ms": test_ms, "other_kernels_ms": kt["table_ms"] / reps,
             "bytes_per_test": path_bytes / (S * G),
-            "roofline_frac": path_bytes / (test_ms * 1e-3) / 1e9 / peak if test_ms > 0 else None,
+            "roofline_frac": path_bytes / ((test_ms + kt["table_ms"] / reps) * 1e-3) / 1e9 / peak if test_ms > 0 else None,
             "l2": l2_note, "parity": parity}
 
 

@@ -42,7 +42,7 @@ extern "C" {
 #define SPADE_HOST 0
 #define SPADE_DEVICE 1
 
-#define SPADE_ABI_VERSION 3
+#define SPADE_ABI_VERSION 4
 
 typedef struct spade_engine spade_engine;
 
@@ -296,12 +296,14 @@ int spade_hypergeom(int device, const int64_t *k, const int64_t *M, const int64_
  * device per table_location), the first G columns are used; sign = -1 for log p tables.
  * Host outputs A, B, C (shape, loc, scale), float64[G], and optionally status int32[G]:
  * 0 fitted, 1 skipped (<= 50 finite values; A = B = C = 0 as the reference leaves them),
- * 2 all values equal (nan, 0, 1), 3 scipy would raise FitError (nan, nan, nan).
+ * 2 all values equal (nan, 0, 1), 3 scipy would raise FitError (nan, nan, nan); and optionally
+ * evals int32[G]: likelihood evaluations used (600 = the budget of scipy's fmin exhausted).
  * Parameters agree with scipy's to the optimiser's own tolerance (1e-4) wherever its optimum
- * is stable; see tests/test_gamma_fit.py.
+ * is stable; see tests/test_gamma_fit.py and DESIGN.md section 7 for the measured agreement.
  */
 int spade_gamma_fit(int device, const double *table, int table_location, int64_t S, int64_t G,
-                    int64_t ld, double sign, double *A, double *B, double *C, int32_t *status);
+                    int64_t ld, double sign, double *A, double *B, double *C, int32_t *status,
+                    int32_t *evals);
 
 /*
  * Significance scoring of observed regions against the DErand background - the arithmetic of

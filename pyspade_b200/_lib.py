@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("SPADE_LIB") or os.path.join(_PKG, "libspade_b200.so")
 
 SPADE_OK, SPADE_ERR_ARG, SPADE_ERR_CUDA, SPADE_ERR_STATE = 0, 1, 2, 3
 SPADE_HOST, SPADE_DEVICE = 0, 1
-SPADE_ABI_VERSION = 3
+SPADE_ABI_VERSION = 4
 SPADE_OPT_TAIL_TABLE, SPADE_OPT_MEMBER_BLOCK, SPADE_OPT_GENES_PER_PART, SPADE_OPT_SORT_MEMBERS = 1, 2, 3, 4
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -81,7 +81,7 @@ SIGNATURES = {
                                        ctypes.c_void_p]),
     "spade_gamma_fit": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                        ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
-                                       ctypes.c_void_p, ctypes.c_void_p]),
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "spade_score": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                    ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -95,9 +95,13 @@ SPADE_HD inline double gamma_penalized_nnlf(const GammaColumn &c, int n, double 
 
 // Status: 0 = fitted, 1 = skipped (<= 50 finite values: outputs untouched zeros),
 //         2 = all finite values equal -> (nan, 0, 1), 3 = scipy would raise FitError -> nan.
+// *evals (optional): likelihood evaluations the simplex used; 600 = scipy's budget exhausted (its
+// fmin then stops with "maximum number of function evaluations exceeded" and returns the best
+// vertex - the fits that are least reproducible across libm / summation-order differences).
 template <class Reduce>
-SPADE_HD inline int gamma_fit_column(const GammaColumn &c, double out[3], const Reduce &red)
+SPADE_HD inline int gamma_fit_column(const GammaColumn &c, double out[3], const Reduce &red, int *evals = nullptr)
 {
+    if (evals) *evals = 0;
     // ---- census: count, mean, min, max, all-equal (DErand.py:268-272) ----
     int n = 0;
     double sum = 0.0, lo = INFINITY, hi = -INFINITY;
@@ -226,6 +230,7 @@ SPADE_HD inline int gamma_fit_column(const GammaColumn &c, double out[3], const 
         }
         sort_simplex();
     }
+    if (evals) *evals = fcalls;
     const double a = sim[0][0], loc = sim[0][1], scale = sim[0][2];
     const double obj = gamma_penalized_nnlf(c, n, a, loc, scale, red);
     if (!(a > 0.0 && scale > 0.0) || !gf_finite(obj)) {          // scipy raises FitError here

@@ -132,8 +132,8 @@ struct spade_engine {
     int64_t tab_epoch = -1, bg_epoch = 0;
     PinnedBuf<TabMeta> h_tmeta;
     PinnedBuf<int64_t> h_offsets, h_sizes;
-    PinnedBuf<int32_t> h_order;
-    DevBuf<int32_t> order;             // ragged batches: sets by decreasing size
+    PinnedBuf<int32_t> h_order, h_order_x;
+    DevBuf<int32_t> order, order_x;    // ragged batches: sets by decreasing size (_x: spade_expand's own copy)
     DevBuf<int64_t> sizes;             // spade_expand's own upload buffers (it may run on another stream)
 
     std::vector<TimedSpan> spans;
@@ -485,15 +485,15 @@ struct spade_engine {
 
     // up / down of rows [0, Sb) x genes [g0, g1) from the counts the test kernel left in k
     // (ragged batches, see k_tails_direct).  sizes: device N per row, or null -> offsets of set s0.
-    int launch_tails(cudaStream_t st, const int32_t *k, int64_t k_ld, const int64_t *sizes, int64_t s0, int64_t Sb,
-                     int64_t g0, int64_t g1, int64_t col0, double *up, double *down, int64_t ld)
+    int launch_tails(cudaStream_t st, const int32_t *k, int64_t k_ld, const int64_t *sizes, const int32_t *by_size,
+                     int64_t s0, int64_t Sb, int64_t g0, int64_t g1, int64_t col0, double *up, double *down, int64_t ld)
     {
         if (Sb <= 0 || g1 <= g0 || (!up && !down)) return SPADE_OK;
         int rc = span_begin(st, 2);
         if (rc != SPADE_OK) return rc;
-        const dim3 grid((unsigned)((g1 - g0 + 255) / 256), (unsigned)std::min<int64_t>(Sb, 65535));
-        k_tails_direct<<<grid, 256, 0, st>>>(k, k_ld, meta.p, sizes, sizes ? nullptr : offsets.p + s0, (int)C, lf.p, up,
-                                             down, ld, Sb, g0, g1, col0);
+        const dim3 grid((unsigned)((g1 - g0 + 7) / 8), (unsigned)std::min<int64_t>((Sb + 31) / 32, 64));
+        k_tails_direct<<<grid, 256, 0, st>>>(k, k_ld, meta.p, sizes, sizes ? nullptr : offsets.p + s0, by_size, (int)C,
+                                             lf.p, up, down, ld, Sb, g0, g1, col0);
         CUDA_TRY(cudaGetLastError());
         rc = span_end(st);
         if (rc != SPADE_OK) return rc;
@@ -568,7 +568,9 @@ struct spade_engine {
         h_offsets.release();
         h_sizes.release();
         h_order.release();
+        h_order_x.release();
         order.release();
+        order_x.release();
         sizes.release();
         for (int i = 0; i < 2; ++i) {
             if (work[i]) cudaStreamDestroy(work[i]);
@@ -1046,7 +1048,7 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             int rc = engine->launch_fused(a, false, st);
             if (rc != SPADE_OK) return rc;
             if (defer) {
-                rc = engine->launch_tails(st, t_k, t_kld, nullptr, s0, Sb, 0, G, 0, t_up, t_down, a.fin.ld);
+                rc = engine->launch_tails(st, t_k, t_kld, nullptr, a.order, s0, Sb, 0, G, 0, t_up, t_down, a.fin.ld);
                 if (rc != SPADE_OK) return rc;
             }
             if (!raw) {
@@ -1068,7 +1070,7 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
                 int rc = engine->launch_fused(a, false, ws);
                 if (rc != SPADE_OK) return rc;
                 if (defer) {
-                    rc = engine->launch_tails(ws, t_k, t_kld, nullptr, s0, Sb, (int64_t)a.p0 * engine->Gp,
+                    rc = engine->launch_tails(ws, t_k, t_kld, nullptr, a.order, s0, Sb, (int64_t)a.p0 * engine->Gp,
                                               std::min<int64_t>(G, (int64_t)a.p1 * engine->Gp), 0, t_up, t_down, a.fin.ld);
                     if (rc != SPADE_OK) return rc;
                 }
@@ -1248,8 +1250,18 @@ int spade_expand_block(spade_engine *engine, const uint64_t *raw, int64_t rows, 
     if (rc != SPADE_OK) return rc;
     engine->launches += 1;
     if (defer) {
-        rc = engine->launch_tails(st, t_k, t_kld, engine->sizes.p, 0, rows, gene_begin, gene_begin + gene_count,
-                                  gene_begin, up, down, out_row_stride);
+        const int32_t *by_size = nullptr;
+        if (rows <= 0x7fffffff) {                          // rows by decreasing set size (see k_tails_direct)
+            CUDA_TRY(engine->h_order_x.reserve((size_t)rows));
+            CUDA_TRY(engine->order_x.reserve((size_t)rows));
+            int32_t *o = engine->h_order_x.p;
+            for (int64_t i = 0; i < rows; ++i) o[i] = (int32_t)i;
+            std::stable_sort(o, o + rows, [&](int32_t x, int32_t y) { return set_sizes[x] > set_sizes[y]; });
+            CUDA_TRY(engine->h_order_x.upload(engine->order_x.p, (size_t)rows, st));
+            by_size = engine->order_x.p;
+        }
+        rc = engine->launch_tails(st, t_k, t_kld, engine->sizes.p, by_size, 0, rows, gene_begin,
+                                  gene_begin + gene_count, gene_begin, up, down, out_row_stride);
         if (rc != SPADE_OK) return rc;
     }
     return SPADE_OK;
@@ -1400,7 +1412,8 @@ constexpr int kGammaGenes = 4;
 
 __global__ void __launch_bounds__(kGammaGenes * 32)
 k_gamma_fit(const double *__restrict__ tab, int S, int64_t G, int64_t ld, double sign, double *__restrict__ A,
-            double *__restrict__ B, double *__restrict__ C, int32_t *__restrict__ status, int use_smem)
+            double *__restrict__ B, double *__restrict__ C, int32_t *__restrict__ status,
+            int32_t *__restrict__ evals, int use_smem)
 {
     extern __shared__ double cols[];                       // [kGammaGenes][S]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1422,9 +1435,11 @@ k_gamma_fit(const double *__restrict__ tab, int S, int64_t G, int64_t ld, double
     col.lane = lane;
     col.nlanes = 32;
     double out[3];
-    const int st = gamma_fit_column(col, out, WarpReduce());
+    int ne = 0;
+    const int st = gamma_fit_column(col, out, WarpReduce(), &ne);
     if (lane == 0) {
         status[g] = st;
+        evals[g] = ne;
         A[g] = out[0];
         B[g] = out[1];
         C[g] = out[2];
@@ -1433,7 +1448,7 @@ k_gamma_fit(const double *__restrict__ tab, int S, int64_t G, int64_t ld, double
 }  // namespace
 
 int spade_gamma_fit(int device, const double *table, int table_location, int64_t S, int64_t G, int64_t ld,
-                    double sign, double *A, double *B, double *C, int32_t *status)
+                    double sign, double *A, double *B, double *C, int32_t *status, int32_t *evals)
 {
     auto fail = [&](int code, const std::string &m) { g_create_error = m; return code; };
     if (S < 0 || G < 0 || ld < G || S > 0x7fffffff || (S > 0 && G > 0 && !table) || (G > 0 && (!A || !B || !C)))
@@ -1458,17 +1473,18 @@ int spade_gamma_fit(int device, const double *table, int table_location, int64_t
         ld = G;
     }
     G_TRY(dout.reserve(3 * (size_t)G));
-    G_TRY(dst.reserve((size_t)G));
+    G_TRY(dst.reserve(2 * (size_t)G));
     const size_t tile = (size_t)kGammaGenes * (size_t)S * sizeof(double);
     const int use_smem = tile <= 96 * 1024;
     if (use_smem) G_TRY(cudaFuncSetAttribute(k_gamma_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     k_gamma_fit<<<(unsigned)((G + kGammaGenes - 1) / kGammaGenes), kGammaGenes * 32, use_smem ? tile : 0>>>(
-        dt, (int)S, G, ld, sign, dout.p, dout.p + G, dout.p + 2 * G, dst.p, use_smem);
+        dt, (int)S, G, ld, sign, dout.p, dout.p + G, dout.p + 2 * G, dst.p, dst.p + G, use_smem);
     G_TRY(cudaGetLastError());
     G_TRY(cudaMemcpy(A, dout.p, G * sizeof(double), cudaMemcpyDeviceToHost));
     G_TRY(cudaMemcpy(B, dout.p + G, G * sizeof(double), cudaMemcpyDeviceToHost));
     G_TRY(cudaMemcpy(C, dout.p + 2 * G, G * sizeof(double), cudaMemcpyDeviceToHost));
     if (status) G_TRY(cudaMemcpy(status, dst.p, G * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (evals) G_TRY(cudaMemcpy(evals, dst.p + G, G * sizeof(int32_t), cudaMemcpyDeviceToHost));
 #undef G_TRY
     return SPADE_OK;
 }

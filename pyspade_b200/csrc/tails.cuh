@@ -94,21 +94,27 @@ k_tail_table(const TabMeta *__restrict__ tmeta, const GeneMeta *__restrict__ met
 }
 
 // Direct tails of finished counts, for batches whose sets differ in size (DEobs: no tail table).
-// The fused kernel leaves k[row][gene]; here one thread per test evaluates hyper_tails at full
-// occupancy (the fused kernel keeps 8 KB of shared memory per warp and 24 warps per SM, which
-// starves this FP64-bound step).  Rows [0, S), genes [g0, g1); sizes[row] = N of the row's set
-// (or offsets[row + 1] - offsets[row] when sizes is null).
+// The fused kernel leaves k[row][gene]; here hyper_tails runs at full occupancy (the fused kernel
+// keeps 8 KB of shared memory per warp and 24 warps per SM, which starves this FP64-bound step).
+// A warp takes ONE gene and 32 sets that are neighbours in the order by set size: its lanes then
+// share n and have similar N and k, so their tail series have nearly the same length (with
+// 32 neighbouring genes per warp the dense genes' long series would stall the sparse genes'
+// short ones).  Rows [0, S), genes [g0, g1); sizes[row] = N of the row's set (or offsets[row + 1]
+// - offsets[row] when sizes is null); order[i] = row of rank i by size (null: identity).
 __global__ void __launch_bounds__(256)
 k_tails_direct(const int32_t *__restrict__ k, int64_t k_ld, const GeneMeta *__restrict__ meta,
-               const int64_t *__restrict__ sizes, const int64_t *__restrict__ offsets, int M,
-               const double *__restrict__ lf, double *__restrict__ up, double *__restrict__ down, int64_t ld,
-               int64_t S, int64_t g0, int64_t g1, int64_t col0)
+               const int64_t *__restrict__ sizes, const int64_t *__restrict__ offsets,
+               const int32_t *__restrict__ order, int M, const double *__restrict__ lf,
+               double *__restrict__ up, double *__restrict__ down, int64_t ld, int64_t S, int64_t g0,
+               int64_t g1, int64_t col0)
 {
-    const int64_t g = g0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = g0 + blockIdx.x * (int64_t)(blockDim.x >> 5) + warp;
     if (g >= g1) return;
     const int n = meta[g].n;
     const int64_t col = g - col0;                          // column of gene g in k / up / down
-    for (int64_t row = blockIdx.y; row < S; row += gridDim.y) {
+    for (int64_t i = blockIdx.y * 32 + lane; i < S; i += (int64_t)gridDim.y * 32) {
+        const int64_t row = order ? order[i] : i;
         const long long N = sizes ? sizes[row] : offsets[row + 1] - offsets[row];
         const int kk = k[row * k_ld + col];
         double lc, ls;

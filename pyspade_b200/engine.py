@@ -411,10 +411,10 @@ def hypergeom_logcdf_logsf(k, M, n, N, device=0):
     return lc.reshape(shape), ls.reshape(shape)
 
 
-def gamma_fit(table, sign=-1.0, device=0):
+def gamma_fit(table, sign=-1.0, device=0, with_evals=False):
     """``spade_gamma_fit``: per-gene ``scipy.stats.gamma.fit`` of ``sign * table[:, g]`` (finite
     values only) on the GPU.  ``table``: float64 ``[S, G]`` numpy array (or CUDA torch tensor).
-    Returns ``(A, B, C, status)``."""
+    Returns ``(A, B, C, status)``, plus ``evals`` (likelihood evaluations per gene) on request."""
     lib = _lib.load()
     if isinstance(table, np.ndarray):
         t = np.ascontiguousarray(table, dtype=np.float64)
@@ -427,10 +427,12 @@ def gamma_fit(table, sign=-1.0, device=0):
     ld = G if isinstance(table, np.ndarray) or S <= 1 else table.stride(0)
     A, B, C = np.zeros(G), np.zeros(G), np.zeros(G)
     status = np.zeros(G, dtype=np.int32)
-    rc = lib.spade_gamma_fit(int(device), ptr, loc, S, G, ld, float(sign), _ptr(A), _ptr(B), _ptr(C), _ptr(status))
+    evals = np.zeros(G, dtype=np.int32)
+    rc = lib.spade_gamma_fit(int(device), ptr, loc, S, G, ld, float(sign), _ptr(A), _ptr(B), _ptr(C), _ptr(status),
+                             _ptr(evals))
     if rc != _lib.SPADE_OK:
         raise SpadeError(f"spade_gamma_fit failed ({rc}): {lib.spade_last_error(None).decode()}")
-    return A, B, C, status
+    return (A, B, C, status, evals) if with_evals else (A, B, C, status)
 
 
 def column_mean(table, device=0):

@@ -61,7 +61,7 @@ def main():
     for d in ("up", "down"):
         table = out[d][:, torch.from_numpy(pick).to(dev)].contiguous()
         t0 = time.perf_counter()
-        A, B, C, st = gamma_fit(table)
+        A, B, C, st, evals = gamma_fit(table, with_evals=True)
         res[f"{d}_device_s"] = time.perf_counter() - t0
         host = table.cpu().numpy()
         neg = -host
@@ -87,6 +87,17 @@ def main():
               "q99": np.nanquantile(x, 0.99, axis=0), "max": np.nanmax(x, axis=0)}
         qs["2max"] = 2.0 * qs["max"]
         qs["4max"] = 4.0 * qs["max"]
+        res[f"{d}_evals_hist"] = {str(b): int(((evals[fitted] >= b) & (evals[fitted] < b + 100)).sum())
+                                  for b in range(0, 700, 100)}
+        capped = evals[fitted] >= 600
+        res[f"{d}_capped_frac"] = float(capped.mean())
+        bad_params = ~(rel <= 1e-3).all(axis=1)
+        res[f"{d}_params_disagree_frac"] = float(bad_params.mean())
+        res[f"{d}_params_disagree_that_are_capped"] = float((bad_params & capped).sum() / max(1, bad_params.sum()))
+        for thr in (300, 400, 500):
+            flag = evals[fitted] >= thr
+            res[f"{d}_evals_ge_{thr}"] = {"flagged_frac": float(flag.mean()),
+                                          "covers_disagree": float((bad_params & flag).sum() / max(1, bad_params.sum()))}
         for name, q in qs.items():
             with np.errstate(all="ignore"):
                 s_dev = stats.gamma.logsf(q[fitted], A[fitted], B[fitted], C[fitted])
@@ -94,6 +105,10 @@ def main():
             diff = np.abs(s_dev - s_ref)
             ok = np.isfinite(diff)
             reld = diff[ok] / np.maximum(np.abs(s_ref[ok]), 1e-3)
+            bad_score = np.zeros(fitted.sum(), dtype=bool)
+            bad_score[ok] = reld > 1e-3
+            res[f"{d}_score_{name}_disagree_that_are_capped"] = float((bad_score & capped).sum() / max(1, bad_score.sum()))
+            res[f"{d}_score_{name}_uncapped_frac_rel_le_1e-3"] = float(np.mean(~bad_score[~capped])) if (~capped).any() else None
             res[f"{d}_score_{name}"] = {
                 "abs_median": float(np.median(diff[ok])), "abs_p99": float(np.quantile(diff[ok], 0.99)),
                 "abs_max": float(diff[ok].max()),
