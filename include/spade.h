@@ -42,7 +42,7 @@ extern "C" {
 #define SPADE_HOST 0
 #define SPADE_DEVICE 1
 
-#define SPADE_ABI_VERSION 4
+#define SPADE_ABI_VERSION 5
 
 typedef struct spade_engine spade_engine;
 
@@ -270,12 +270,17 @@ int spade_ipc_open(int device, const unsigned char handle[64], void **dptr);
 int spade_ipc_close(int device, void *dptr);
 
 /* Kernel-time accounting (CUDA events on the launch streams, accumulated since the last
- * reset).  test_ms = the fused test kernel (member accumulation + tails + table writes),
- * table_ms = everything else spade_run / spade_expand launch (tail-table builds, split-path
- * finalize, expansion of raw words).  Synchronises.
- * launches = kernels launched by spade_run. */
+ * reset).  test_ms = the test itself: k_de_fused (member accumulation, and tails + table writes
+ * when it finishes its tests itself) plus, for uniform batches with device tables, the k_expand
+ * launch that finishes its accumulator words (two-phase form);
+ * table_ms = everything else spade_run / spade_expand launch (tail-table builds, direct tails of
+ * ragged batches, split-path finalize, expansion of raw words received from other GPUs).
+ * Synchronises.  launches = kernels launched by spade_run.
+ * spade_timing_finish: the part of test_ms spent in the finishing launch of two-phase runs
+ * (same accumulation period; reset by spade_timing). */
 int spade_timing(spade_engine *engine, double *test_ms, double *table_ms, int64_t *launches,
                  int reset);
+int spade_timing_finish(spade_engine *engine, double *finish_ms);
 
 /*
  * K3 in isolation (parity probe): logcdf / logsf of scipy.stats.hypergeom for `count`

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("SPADE_LIB") or os.path.join(_PKG, "libspade_b200.so")
 
 SPADE_OK, SPADE_ERR_ARG, SPADE_ERR_CUDA, SPADE_ERR_STATE = 0, 1, 2, 3
 SPADE_HOST, SPADE_DEVICE = 0, 1
-SPADE_ABI_VERSION = 4
+SPADE_ABI_VERSION = 5
 SPADE_OPT_TAIL_TABLE, SPADE_OPT_MEMBER_BLOCK, SPADE_OPT_GENES_PER_PART, SPADE_OPT_SORT_MEMBERS = 1, 2, 3, 4
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -76,6 +76,7 @@ SIGNATURES = {
     "spade_check": (ctypes.c_int, [ctypes.c_void_p]),
     "spade_wide_genes": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
     "spade_timing": (ctypes.c_int, [ctypes.c_void_p, c_f64p, c_f64p, c_i64p, ctypes.c_int]),
+    "spade_timing_finish": (ctypes.c_int, [ctypes.c_void_p, c_f64p]),
     "spade_hypergeom": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                        ctypes.c_void_p]),

@@ -181,7 +181,69 @@ __device__ __forceinline__ void decode_entry(unsigned long long e, uint32_t &slo
     add = ((unsigned long long)(uint32_t)hs << 32) | (uint32_t)e;
 }
 
-template <bool kSplit>
+// The register accumulators of the dense head join the shared-memory ones.
+__device__ __forceinline__ void hand_over_dense(const RunArgs &a, unsigned long long *acc,
+                                                const unsigned long long (&dacc)[kDenseRegs], bool dense, int lane,
+                                                int p, int64_t g0)
+{
+    if (!dense) return;
+#pragma unroll
+    for (int w2 = 0; w2 < kDenseRegs; ++w2) {
+        const int32_t dg = a.dgene[p * kDenseLanes + lane + 32 * w2];
+        if (dg >= 0) acc[dg - g0] = dacc[w2];
+    }
+    __syncwarp();
+}
+
+// What a warp does with the finished accumulators of its (partition p, set `row`) task: the raw
+// words to the owner of the gene block (routed), the raw words to one table, or the finished tests.
+// kRawOnly: instantiation without the finalize code (raw forms only; fewer registers).
+template <bool kRawOnly = false>
+__device__ __forceinline__ void finish_task(const RunArgs &a, const unsigned long long *acc, int lane, int p,
+                                            int64_t g0, int ng, int64_t row, long long N)
+{
+    // the accumulator word of gene j of the partition (count << 48 | sum)
+    auto word = [&](int j) -> unsigned long long {
+        return a.two ? acc[j] + acc[a.Gp + alt_slot(j)] : acc[j];
+    };
+    if (a.ndst > 0) {
+        // raw form, routed: this partition's words go to the owner of its gene block (a table in
+        // this GPU's or a peer GPU's memory; coalesced 256-byte stores over NVLink)
+        int b = 0;
+        while (b + 1 < a.ndst && p >= a.dst_pbegin[b + 1]) ++b;
+        unsigned long long *dst = a.dst_base[b] + (a.raw_row0 + row * a.raw_row_step) * a.dst_ld[b] +
+                                  (g0 - (int64_t)a.dst_pbegin[b] * a.Gp);
+        for (int j = lane; j < ng; j += 32) dst[j] = word(j);
+    } else if (kRawOnly || a.raw) {
+        // raw form: the accumulator words leave as they are (8 bytes per test instead of 24-36);
+        // whoever receives them finishes the tests with k_expand
+        for (int j = lane; j < ng; j += 32) a.raw[row * a.raw_ld + g0 + j] = word(j);
+    } else if (!kRawOnly) {
+        const double invN = 1.0 / (double)N;
+        const double invRest = 1.0 / (double)((long long)a.C - N);
+        // kFinBatch genes per lane at a time: their metadata / table loads overlap
+        for (int j0 = lane; j0 < ng; j0 += 32 * kFinBatch) {
+            FinItem it[kFinBatch];
+#pragma unroll
+            for (int u = 0; u < kFinBatch; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < ng) {
+                    const long long v = (long long)word(j);
+                    const long long sumfx = (v << 16) >> 16;
+                    const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
+                    fin_load(a.fin, g0 + j, sumfx, cnt, N, it[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kFinBatch; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < ng) fin_store(a.fin, row, g0 + j, it[u], N, invN, invRest);
+            }
+        }
+    }
+}
+
+template <bool kSplit, bool kRawOnly = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(const RunArgs a)
 {
     extern __shared__ unsigned long long smem_acc[];
@@ -213,11 +275,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     const int ng = (int)min((int64_t)a.Gp, a.fin.G - g0);
     for (int j = lane; j < a.acc_len; j += 32) acc[j] = 0ull;
     __syncwarp();
-    // the accumulator word of gene j of the partition (count << 48 | sum)
-    auto word = [&](int j) -> unsigned long long {
-        return a.two ? acc[j] + acc[a.Gp + alt_slot(j)] : acc[j];
-    };
-
     const uint2 *__restrict__ seg = a.seg + (int64_t)p * a.C;
     const int32_t *__restrict__ mem = a.members + mbeg;
     const unsigned long long *__restrict__ ent = a.ent;
@@ -321,52 +378,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
             process(A);
         }
     }
-    if (dense) {                   // hand the register accumulators to the common finalize
-#pragma unroll
-        for (int w2 = 0; w2 < kDenseRegs; ++w2) {
-            const int32_t dg = a.dgene[p * kDenseLanes + lane + 32 * w2];
-            if (dg >= 0) acc[dg - g0] = dacc[w2];
-        }
-        __syncwarp();
-    }
-
-    if (!kSplit && a.ndst > 0) {
-        // raw form, routed: this partition's words go to the owner of its gene block (a table in
-        // this GPU's or a peer GPU's memory; coalesced 256-byte stores over NVLink)
-        int b = 0;
-        while (b + 1 < a.ndst && p >= a.dst_pbegin[b + 1]) ++b;
-        unsigned long long *dst = a.dst_base[b] + (a.raw_row0 + row * a.raw_row_step) * a.dst_ld[b] +
-                                  (g0 - (int64_t)a.dst_pbegin[b] * a.Gp);
-        for (int j = lane; j < ng; j += 32) dst[j] = word(j);
-    } else if (!kSplit && a.raw) {
-        // raw form: the accumulator words leave as they are (8 bytes per test instead of 24-36);
-        // whoever receives them finishes the tests with k_expand
-        for (int j = lane; j < ng; j += 32) a.raw[row * a.raw_ld + g0 + j] = word(j);
-    } else if (!kSplit) {
-        const double invN = 1.0 / (double)N;
-        const double invRest = 1.0 / (double)((long long)a.C - N);
-        // kFinBatch genes per lane at a time: their metadata / table loads overlap
-        for (int j0 = lane; j0 < ng; j0 += 32 * kFinBatch) {
-            FinItem it[kFinBatch];
-#pragma unroll
-            for (int u = 0; u < kFinBatch; ++u) {
-                const int j = j0 + 32 * u;
-                if (j < ng) {
-                    const long long v = (long long)word(j);
-                    const long long sumfx = (v << 16) >> 16;
-                    const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
-                    fin_load(a.fin, g0 + j, sumfx, cnt, N, it[u]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kFinBatch; ++u) {
-                const int j = j0 + 32 * u;
-                if (j < ng) fin_store(a.fin, row, g0 + j, it[u], N, invN, invRest);
-            }
-        }
+    hand_over_dense(a, acc, dacc, dense, lane, p, g0);
+    if (!kSplit) {
+        finish_task<kRawOnly>(a, acc, lane, p, g0, ng, row, N);
     } else {
         for (int j = lane; j < ng; j += 32) {
-            const long long v = (long long)word(j);
+            const long long v = (long long)(a.two ? acc[j] + acc[a.Gp + alt_slot(j)] : acc[j]);
             if (v == 0) continue;
             const long long sumfx = (v << 16) >> 16;
             const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
@@ -441,7 +458,8 @@ __global__ void k_check_duplicates(const int32_t *__restrict__ sorted, const int
 }
 
 // Finish tests from raw accumulator words (k_de_fused raw form), e.g. words another GPU stored
-// into this GPU's memory.  sizes[row] = N of the row's cell set.  A thread owns one gene and
+// into this GPU's memory.  sizes[row] = N of the row's cell set (sizes null: offsets[row + 1] -
+// offsets[row], the offsets of the batch the words came from).  A thread owns one gene and
 // walks kExpandRows rows: the gene's metadata is read once, raw reads and table writes are
 // coalesced across the genes of a warp.
 constexpr int kExpandRows = 16;
@@ -449,7 +467,8 @@ constexpr int kExpandRows = 16;
 // Gene block [g_begin, g_begin + g_count): column j of raw and of the tables = gene g_begin + j.
 __global__ void __launch_bounds__(256)
 k_expand(const FinCtx f, const unsigned long long *__restrict__ raw, int64_t raw_ld,
-         const int64_t *__restrict__ sizes, int64_t rows, int64_t g_begin, int64_t g_count)
+         const int64_t *__restrict__ sizes, const int64_t *__restrict__ offsets, int64_t rows, int64_t g_begin,
+         int64_t g_count)
 {
     const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (col >= g_count) return;
@@ -471,7 +490,7 @@ k_expand(const FinCtx f, const unsigned long long *__restrict__ raw, int64_t raw
         const long long v = (long long)w[i];
         const long long sumfx = (v << 16) >> 16;
         const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);
-        const long long N = sizes[row];
+        const long long N = sizes ? sizes[row] : offsets[row + 1] - offsets[row];
         const int kk = mt.negmode ? cnt : (int)(N - cnt);
         const double mean_set = fixed_mean(sumfx, mt.shift, 1.0 / (double)N);
         const int64_t o = row * f.ld + col;

@@ -389,10 +389,13 @@ class Engine:
         return n.value
 
     def timing(self, reset=False):
-        a, f, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        """Kernel times since the last reset (``spade_timing``): ``test_ms`` = the test kernels,
+        of which ``finish_ms`` in the finishing launch of two-phase runs; ``table_ms`` = the rest."""
+        a, f, n, x = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+        self._check(self._lib.spade_timing_finish(self._h, ctypes.byref(x)))
         self._check(self._lib.spade_timing(self._h, ctypes.byref(a), ctypes.byref(f),
                                            ctypes.byref(n), 1 if reset else 0))
-        return dict(test_ms=a.value, table_ms=f.value, launches=n.value)
+        return dict(test_ms=a.value, table_ms=f.value, finish_ms=x.value, launches=n.value)
 
 
 def hypergeom_logcdf_logsf(k, M, n, N, device=0):

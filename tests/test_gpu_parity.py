@@ -355,6 +355,42 @@ def test_layout_switches_do_not_change_results(monkeypatch):
     assert_tables_close(res[(1, 1)][1], ora)
 
 
+def test_kernel_forms_do_not_change_results(monkeypatch):
+    """Device tables of a uniform batch come from two launches (k_de_fused leaves accumulator
+    words, k_expand finishes them); SPADE_TWO_PHASE=0 keeps the finalize inside the test kernel
+    and SPADE_TMA=1 stages the segments through the TMA unit (k_de_tma): all bit-identical to
+    the host-output run, which always finishes its tests inside the kernel."""
+    import torch
+    from pyspade_b200 import synth
+    from pyspade_b200.engine import Engine
+    G, C = 2300, 1800
+    counts = synth.counts_numpy(G, C, seed=29)
+    nc = np.arange(3, C, 11)
+    batches = (synth.derand_draws(C, 77, 40), synth.deobs_sets(C, 9, lo=5, hi=1200))
+    with Engine.from_counts(counts) as eng:
+        want = [eng.run(sets, want_k=True) for sets in batches]
+        eng.set_background(nc)
+        want_nc = [eng.run(sets, want_k=True) for sets in batches]
+    for two_phase, tma, two_choice in ((1, 0, 0), (0, 0, 0), (1, 1, 0), (0, 1, 0), (1, 1, 1), (0, 1, 1)):
+        monkeypatch.setenv("SPADE_TWO_PHASE", str(two_phase))
+        monkeypatch.setenv("SPADE_TMA", str(tma))
+        monkeypatch.setenv("SPADE_TWO_CHOICE", str(two_choice))
+        with Engine.from_counts(counts) as eng:
+            for bg, ref in ((None, want), (nc, want_nc)):
+                eng.set_background(bg)
+                for sets, w in zip(batches, ref):
+                    members, offsets = synth.concat_sets(sets)
+                    dm = torch.from_numpy(members).cuda()
+                    out = {t: torch.empty((len(sets), G), dtype=torch.float64, device="cuda")
+                           for t in ("up", "down", "fc", "cpm")}
+                    kd = torch.empty((len(sets), G), dtype=torch.int32, device="cuda")
+                    eng.run_device(dm, offsets, out, k=kd)
+                    eng.check()
+                    got = {t: v.cpu().numpy() for t, v in out.items()}
+                    got["k"] = kd.cpu().numpy()
+                    _tables_equal({t: w[t] for t in got}, got)
+
+
 @pytest.mark.parametrize("mode", ["complement", "nc"])
 def test_raw_form_and_expand_equal_direct_run(mode):
     """spade_run_raw + spade_expand (what a peer GPU sends / what rank 0 finishes) give the
