@@ -540,6 +540,17 @@ def main():
         sampler.start()
     dev_ms, _, kt, win_a = timed(step_device, args.steps, args.warmup)
     _, e2e_ms, _, win_b = timed(step_e2e, args.steps, args.warmup)
+    # what the link gives: the same tables as three plain device -> host copies, nothing else
+    link_gbs = None
+    if world == 1:
+        import ctypes
+
+        def plain_copies(i):
+            for k in TABLES:
+                lib.spade_memcpy2d(ctypes.c_void_p(host_out[k].ctypes.data), 8 * G, ctypes.c_void_p(out_dev[k].data_ptr()),
+                                   8 * G, 8 * G, S, 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        copy_ms, _, _, _ = timed(plain_copies, 3, 1)
+        link_gbs = len(TABLES) * S * G * 8 * 3 / (copy_ms * 1e-3) / 1e9
     clocks = sampler.stop([win_a, win_b]) if rank == 0 else None
 
     tests_per_step = S * G * world
@@ -567,7 +578,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("k_de_fused_dram_bytes_per_launch")
+            traffic = json.load(fh).get("step_dram_bytes")        # both launches of the two-phase form
     roofline = {"bound": "hbm", "kernel": "k_de_fused" + (" + k_expand (two-phase form of the test)" if finish_ms > 0 else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic if world == 1 else None, "peak_source": peak_src,
@@ -591,7 +602,9 @@ def main():
                            "stage_seconds": st.stage_s},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "path": e2e_mode,
                         "h2d_bytes_per_step": int(world * (4 * S * N + 8 * (S + 1))),
-                        "d2h_bytes_per_step": int(world * S * G * 8 * len(TABLES))},
+                        "d2h_bytes_per_step": int(world * S * G * 8 * len(TABLES)),
+                        "d2h_gbs": world * S * G * 8 * len(TABLES) / (e2e_ms / args.steps * 1e-3) / 1e9,
+                        "d2h_gbs_plain_copy_of_the_tables": link_gbs},
                 "gpu_launches": int(kt["launches"]),
                 "roofline": roofline, "clocks": clocks}
 

@@ -1075,7 +1075,7 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             int rc;
             if (engine->two_phase && table && !raw) {
                 // Uniform batch (DErand), device tables, two phases: the test kernel leaves its 8-byte accumulator words,
-                // k_expand finishes them with a thread per gene walking 16 sets (gene metadata and
+                // k_expand finishes them with a thread per gene walking 8 sets (gene metadata and
                 // tail-table window reused across the sets, full occupancy): 0.90 -> 0.64 ms per 1 000
                 // draws of 50 cells, 2.23 -> 2.08 ms at 500 cells.  Ragged batches keep the fused
                 // finalize (their tails are deferred anyway; measured 1.58 vs 1.64 ms per 500 regions).

@@ -18,21 +18,24 @@ __device__ __forceinline__ double ln_choose(const double *__restrict__ lf, int a
 // zero (end of the support) or a term drops below kTailEps of the sum.  Division-free: with
 // P_i = prod(fa fb), D_i = prod(fc fd) the sum is N_i / D_i, N_i = N_{i-1} fc fd + P_i; the
 // three running values are rescaled by a power of two every 8 terms (factors are < 2^31, so
-// eight steps grow them by less than 2^500).
+// eight steps grow them by less than 2^500).  The two factor products are stepped by their
+// differences ((fa-1)(fb-1) = fa fb - (fa + fb - 1), (fc+1)(fd+1) = fc fd + (fc + fd + 1): exact
+// integers in double up to 2^53, i.e. for every population below 9.4e7 cells) - 10 instead of
+// 13 float64 operations per term of this FP64-bound loop.
 __device__ __forceinline__ double tail_series(double fa, double fb, double fc, double fd)
 {
     double P = 1.0, D = 1.0, Nn = 1.0;
+    double pab = fa * fb, sab = fa + fb - 1.0, pcd = fc * fd, tcd = fc + fd + 1.0;
     bool more = fa > 0.0 && fb > 0.0;
     while (more) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (more) {
-                const double b = fc * fd;
-                P *= fa * fb;
-                D *= b;
-                Nn = fma(Nn, b, P);
-                fa -= 1.0; fb -= 1.0; fc += 1.0; fd += 1.0;
-                more = fa > 0.0 && fb > 0.0 && !(P < Nn * kTailEps);
+                P *= pab;
+                D *= pcd;
+                Nn = fma(Nn, pcd, P);
+                pab -= sab; sab -= 2.0; pcd += tcd; tcd += 2.0;
+                more = pab > 0.0 && !(P < Nn * kTailEps);
             }
         }
         // exact power-of-two rescale that brings D into [1, 2)

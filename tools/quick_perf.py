@@ -41,7 +41,7 @@ for rep in range(a.reps):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     t = eng.timing()
-    print(f"rep{rep}: total {ms:.2f} ms  test {t['test_ms']:.2f}  table {t['table_ms']:.2f}  "
+    print(f"rep{rep}: total {ms:.3f} ms  test {t['test_ms']:.3f} (finish {t['finish_ms']:.3f})  table {t['table_ms']:.2f}  "
           f"tests/s {a.S*a.G/ms*1e3:.3e}")
 # host path
 t0 = time.time()
