@@ -25,13 +25,12 @@ constexpr int kMemberBlock = 32768;
 // Guaranteed relative accuracy of a fixed-point member mean of same-signed values; genes that
 // cannot meet it take the float64 side path (stage.cuh, wide.cuh).  Fold changes: twice this.
 constexpr double kWideRelBound = 0x1p-22;             // 2.4e-7
-// Two-choice accumulators (stage.cuh k_two_choice): every gene of a partition owns TWO
-// accumulators in different shared-memory bank pairs, A at index slot and B at index
-// Gp + alt_slot(slot); an entry carries the index of the one it adds into, chosen at staging time
-// so that the 16 entries a half-warp handles together never share a bank pair.  The test is
-// finished from A + B.  kTwoDummy spare accumulators (one per bank pair, never read) take the
-// holes of rows that could not be filled.
-constexpr int kTwoDummy = 16;
+// Hot genes (stage.cuh order_segment): the H genes of a partition with the most stored values
+// after the dense head own TWO accumulators in different shared-memory bank pairs, A at index
+// slot and B at index Gp + b (b < H; b mod 16 != slot mod 16); an entry carries the index of the
+// one it adds into, chosen per segment at staging time so that the bank pairs of a segment are
+// asked for as evenly as possible.  The test is finished from A + B.  H = Gp: every gene, B at
+// Gp + alt_slot(slot).
 __host__ __device__ __forceinline__ int alt_slot(int s)    // same 16-group, bank pair shifted by 1..15
 {
     return (s & ~15) | ((s + 1 + ((s >> 4) % 15)) & 15);

@@ -166,8 +166,9 @@ struct RunArgs {
     int64_t raw_row0, raw_row_step;
     int p0, p1;                   // gene partitions of this launch
     int Gp;
-    int two;                      // two-choice accumulators (common.cuh): a test is finished from A + B
-    int acc_len;                  // accumulators per warp: Gp, or 2 Gp + kTwoDummy
+    int two;                      // hot genes per partition (common.cuh), 0 = none: a test is finished from A + B
+    const int16_t *hot_slot;      // [P * two] slot of the gene whose B accumulator is Gp + b, negative = unused
+    int acc_len;                  // accumulators per warp: Gp + two
     int64_t C;
     FinCtx fin;
     int *err;
@@ -181,11 +182,21 @@ __device__ __forceinline__ void decode_entry(unsigned long long e, uint32_t &slo
     add = ((unsigned long long)(uint32_t)hs << 32) | (uint32_t)e;
 }
 
-// The register accumulators of the dense head join the shared-memory ones.
+// The register accumulators of the dense head join the shared-memory ones, and the second
+// accumulators of the hot genes are added into the first.
 __device__ __forceinline__ void hand_over_dense(const RunArgs &a, unsigned long long *acc,
                                                 const unsigned long long (&dacc)[kDenseRegs], bool dense, int lane,
                                                 int p, int64_t g0)
 {
+    if (a.two) {
+        __syncwarp();
+        const int16_t *__restrict__ hs = a.hot_slot + (int64_t)p * a.two;
+        for (int b = lane; b < a.two; b += 32) {
+            const int sl = hs[b];
+            if (sl >= 0) acc[sl] += acc[a.Gp + b];
+        }
+        __syncwarp();
+    }
     if (!dense) return;
 #pragma unroll
     for (int w2 = 0; w2 < kDenseRegs; ++w2) {
@@ -203,9 +214,7 @@ __device__ __forceinline__ void finish_task(const RunArgs &a, const unsigned lon
                                             int64_t g0, int ng, int64_t row, long long N)
 {
     // the accumulator word of gene j of the partition (count << 48 | sum)
-    auto word = [&](int j) -> unsigned long long {
-        return a.two ? acc[j] + acc[a.Gp + alt_slot(j)] : acc[j];
-    };
+    auto word = [&](int j) -> unsigned long long { return acc[j]; };
     if (a.ndst > 0) {
         // raw form, routed: this partition's words go to the owner of its gene block (a table in
         // this GPU's or a peer GPU's memory; coalesced 256-byte stores over NVLink)
@@ -337,6 +346,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
 #pragma unroll
             for (int it = 0; it < kIters; ++it) {
                 const uint32_t i = t.bb[q] + 32 * it;
+                // (the zero is never used, but without it ptxas schedules the batch 8 % slower)
                 t.r[q][it] = i < t.ee[q] ? stream_load(ent + i) : 0ull;
             }
     };
@@ -383,7 +393,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         finish_task<kRawOnly>(a, acc, lane, p, g0, ng, row, N);
     } else {
         for (int j = lane; j < ng; j += 32) {
-            const long long v = (long long)(a.two ? acc[j] + acc[a.Gp + alt_slot(j)] : acc[j]);
+            const long long v = (long long)acc[j];
             if (v == 0) continue;
             const long long sumfx = (v << 16) >> 16;
             const int cnt = (int)((unsigned long long)(v - sumfx) >> kCountShift);

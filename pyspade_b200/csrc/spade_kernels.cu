@@ -85,9 +85,15 @@ struct spade_engine {
     int bank_order = 1;                // lay segments out for conflict-free accumulator access
     int dense_blocks = 1;              // register-accumulated dense block per partition
     int sort_members = 1;              // walk every set in ascending cell order (L2 locality)
-    int two_choice = 0;                // two accumulators per gene, conflict-free rows (common.cuh)
+    int two_choice = 112;              // hot genes per partition with a second accumulator (common.cuh), 0 = none;
+                                       // 112: what fits next to 1 024 first accumulators at 6 CTAs per SM
     int use_tma = 0;                   // test kernel with TMA-staged segments (fused_tma.cuh) instead of k_de_fused
-    int acc_len() const { return two_choice ? 2 * Gp + kTwoDummy : Gp; }
+    int hot() const       // at most Gp, and what the 227 KB of shared memory leave for 4 warps
+    {
+        return std::max(0, std::min(std::min(two_choice, Gp), 227 * 1024 / (8 * kWarpsPerCta) - 32 - Gp)) / 16 * 16;
+    }
+    int acc_len() const { return Gp + hot(); }
+    DevBuf<int16_t> hotb, hot_slot;    // [G] B accumulator of a hot gene (or -1); [P * hot()] its slot
 
     DevBuf<int64_t> indptr;
     DevBuf<int32_t> indices;
@@ -248,15 +254,10 @@ struct spade_engine {
         a.wide_flag = wide_flag.p;
         if (G > 0) k_gene_stage<<<(unsigned)G, kStageThreads, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
-        if (nnz > 0 && two_choice) {
+        if (nnz > 0 && (bank_order || hot() > 0)) {
             const int64_t nseg = (int64_t)P * C;
-            k_two_choice<<<(unsigned)((nseg + kTwoWarps - 1) / kTwoWarps), kTwoWarps * 32, 0, st>>>(
-                seg.p, cursor.p, nseg, C, Gp, dense_on.p, ent.p);
-            CUDA_TRY(cudaGetLastError());
-        } else if (nnz > 0 && bank_order) {
-            const int64_t nseg = (int64_t)P * C;
-            k_bank_order<<<(unsigned)((nseg + kOrderWarps - 1) / kOrderWarps), kOrderWarps * 32, 0, st>>>(
-                seg.p, nseg, C, dense_on.p, ent.p);
+            k_order_segments<<<(unsigned)((nseg + kOrderWarps - 1) / kOrderWarps), kOrderWarps * 32, 0, st>>>(
+                seg.p, nseg, C, Gp, hot(), hotb.p, dense_on.p, ent.p);
             CUDA_TRY(cudaGetLastError());
         }
         h_n.resize((size_t)G);
@@ -284,7 +285,7 @@ struct spade_engine {
 
         Gp = gp_request > 0 ? gp_request : kDefaultGenesPerPart;
         Gp = std::min<int64_t>(Gp, std::max<int64_t>(32, (G + 31) / 32 * 32));
-        Gp = std::max(32, std::min(Gp, two_choice ? 2048 : 4096)) / 32 * 32;
+        Gp = std::max(32, std::min(Gp, 4096)) / 32 * 32;
         P = (int)std::max<int64_t>(1, (G + Gp - 1) / Gp);
         if ((double)P * (double)C + 1 > 4.0e9) {
             set_error("partition index does not fit: (G / genes_per_part) * C must stay below 4e9");
@@ -349,6 +350,53 @@ struct spade_engine {
             CUDA_TRY(cudaMemcpy(dslot.p, hslot.data(), G * sizeof(int8_t), cudaMemcpyHostToDevice));
             CUDA_TRY(cudaMemcpy(dgene.p, hgene.data(), hgene.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
             CUDA_TRY(cudaMemcpy(dense_on.p, hon.data(), P * sizeof(uint8_t), cudaMemcpyHostToDevice));
+
+            // Hot genes: per partition the H genes with the most stored values after the dense head
+            // get a second accumulator Gp + b whose bank pair (b mod 16) differs from the first's.
+            const int H = hot();
+            if (H > 0) {
+                std::vector<int16_t> hb(G, (int16_t)-1), hs((size_t)P * H, (int16_t)-1);
+                std::vector<int64_t> cand;
+                for (int p = 0; p < P; ++p) {
+                    const int64_t g0 = (int64_t)p * Gp, g1 = std::min<int64_t>(G, g0 + Gp);
+                    int16_t *slot_of = hs.data() + (size_t)p * H;
+                    if (H >= Gp) {                           // every gene: B at Gp + alt_slot(slot)
+                        for (int64_t g = g0; g < g1; ++g) {
+                            if (hslot[g] >= 0) continue;
+                            const int b = alt_slot((int)(g - g0));
+                            hb[g] = (int16_t)b;
+                            slot_of[b] = (int16_t)(g - g0);
+                        }
+                        continue;
+                    }
+                    cand.clear();
+                    for (int64_t g = g0; g < g1; ++g)
+                        if (hslot[g] < 0 && hp[g + 1] > hp[g]) cand.push_back(g);
+                    const size_t top = std::min<size_t>((size_t)H, cand.size());
+                    std::partial_sort(cand.begin(), cand.begin() + top, cand.end(), [&](int64_t x, int64_t y) {
+                        const int64_t nx = hp[x + 1] - hp[x], ny = hp[y + 1] - hp[y];
+                        return nx != ny ? nx > ny : x < y;
+                    });
+                    for (size_t i = 0; i < top; ++i) {
+                        const int sl = (int)(cand[i] - g0);
+                        const int want = alt_slot(sl) & 15;
+                        int b = -1;
+                        for (int d = 0; d < 16 && b < 0; ++d) {          // preferred pair first, never the gene's own
+                            const int pair = (want + d) & 15;
+                            if (pair == (sl & 15)) continue;
+                            for (int q = pair; q < H; q += 16)
+                                if (slot_of[q] < 0) { b = q; break; }
+                        }
+                        if (b < 0) continue;                             // only its own pair is left: not hot
+                        hb[cand[i]] = (int16_t)b;
+                        slot_of[b] = (int16_t)sl;
+                    }
+                }
+                CUDA_TRY(hotb.reserve(G));
+                CUDA_TRY(hot_slot.reserve(hs.size()));
+                CUDA_TRY(cudaMemcpy(hotb.p, hb.data(), G * sizeof(int16_t), cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(hot_slot.p, hs.data(), hs.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+            }
         }
 
         // segment sizes per (partition, cell) -> padded to 128-byte lines -> exclusive scan
@@ -362,14 +410,14 @@ struct spade_engine {
                 CUDA_TRY(cudaGetLastError());
             }
             k_pad_counts<<<grid_for(np, 256), 256, 0, st>>>(count.p, (int64_t)np, C, dense_on.p,
-                                                           two_choice ? 16u : 0u, cursor.p);
+                                                           0u, cursor.p);
             CUDA_TRY(cudaGetLastError());
             size_t scan_bytes = 0;
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cursor.p, pptr.p, (int64_t)np, st));
             DevBuf<uint8_t> temp;
             CUDA_TRY(temp.reserve(scan_bytes));
             // padded total <= nnz + (dense head + 15) per segment: must fit the 32-bit entry index
-            if ((unsigned long long)nnz + (unsigned long long)(kSegAlign - 1 + (two_choice ? 16 : 0) + (any_dense ? kDenseLanes : 0)) * np >
+            if ((unsigned long long)nnz + (unsigned long long)(kSegAlign - 1 + (any_dense ? kDenseLanes : 0)) * np >
                 0xffff0000ull) {
                 set_error("matrix too large: padded entry count must stay below 2^32 - 65536");
                 return SPADE_ERR_ARG;
@@ -390,18 +438,18 @@ struct spade_engine {
         if (rc != SPADE_OK) return rc;
 
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kWarpsPerCta * (4096 + kTwoDummy + 32) * 8));
+                                      std::min(227 * 1024, kWarpsPerCta * (2 * 4096 + 32) * 8)));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kWarpsPerCta * (4096 + kTwoDummy + 32) * 8));
+                                      std::min(227 * 1024, kWarpsPerCta * (2 * 4096 + 32) * 8)));
         CUDA_TRY(cudaFuncSetAttribute(k_de_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      std::min(227 * 1024, kTmaWarps * tma_warp_words(4096 + kTwoDummy) * 8)));
+                                      std::min(227 * 1024, kTmaWarps * tma_warp_words(2 * 4096) * 8)));
         CUDA_TRY(cudaFuncSetAttribute(k_de_tma<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUDA_TRY(cudaFuncSetAttribute(k_de_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      std::min(227 * 1024, kTmaWarps * tma_warp_words(4096 + kTwoDummy) * 8)));
+                                      std::min(227 * 1024, kTmaWarps * tma_warp_words(2 * 4096) * 8)));
         CUDA_TRY(cudaFuncSetAttribute(k_de_tma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUDA_TRY(cudaFuncSetAttribute((k_de_fused<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kWarpsPerCta * (4096 + kTwoDummy + 32) * 8));
+                                      std::min(227 * 1024, kWarpsPerCta * (2 * 4096 + 32) * 8)));
         CUDA_TRY(cudaFuncSetAttribute((k_de_fused<false, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUDA_TRY(cudaFuncSetAttribute(k_de_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         return stage_genes(st);
@@ -575,7 +623,7 @@ struct spade_engine {
     void free_all()
     {
         indptr.release(); indices.release(); values.release(); pptr.release(); cursor.release();
-        seg.release(); dslot.release(); dgene.release(); dense_on.release();
+        seg.release(); dslot.release(); dgene.release(); dense_on.release(); hotb.release(); hot_slot.release();
         ent.release(); median.release(); lf.release(); n.release(); meta.release(); ncmask.release();
         wide_flag.release(); wide_genes.release(); bits_buf[0].release(); bits_buf[1].release();
         if (h_err) cudaFreeHost(h_err);
@@ -638,7 +686,7 @@ int create_common(int device, int64_t G, int64_t C, const int64_t *indptr, const
     if (const char *gp = getenv("SPADE_GENES_PER_PART")) e->gp_request = atoi(gp);
     if (const char *bo = getenv("SPADE_BANK_ORDER")) e->bank_order = atoi(bo) != 0;
     if (const char *db = getenv("SPADE_DENSE_BLOCKS")) e->dense_blocks = atoi(db) != 0;
-    if (const char *tc = getenv("SPADE_TWO_CHOICE")) e->two_choice = atoi(tc) != 0;
+    if (const char *tc = getenv("SPADE_TWO_CHOICE")) e->two_choice = atoi(tc) == 1 ? 8192 : atoi(tc);   // 1 = every gene
     if (const char *tm = getenv("SPADE_TMA")) e->use_tma = atoi(tm);   // 1 = cp.async.bulk (TMA), 2 = cp.async (LDGSTS)
     if (const char *tp = getenv("SPADE_TWO_PHASE")) e->two_phase = atoi(tp) != 0;
     auto bail = [&](int code) {
@@ -942,7 +990,8 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
         a.s0 = s0;
         a.S = Sb;
         a.Gp = engine->Gp;
-        a.two = engine->two_choice;
+        a.two = engine->hot();
+        a.hot_slot = engine->hot_slot.p;
         a.acc_len = engine->acc_len();
         a.C = C;
         a.err = engine->d_err;

@@ -286,171 +286,159 @@ __global__ void __launch_bounds__(kStageThreads) k_gene_stage(StageArgs a)
 // ------------------------------------------------------------------------------------------
 // Bank-aware order inside every (partition, cell) segment.  The test kernel reads a segment
 // 32 entries per step and each lane does a 64-bit read-modify-write of its gene's
-// accumulator: the hardware serves that as two half-warps of 16 lanes, conflict-free when
-// the 16 accumulators fall in 16 different 8-byte bank pairs (slot mod 16).  Entry order
-// inside a segment is free (integer adds commute), so the segment is laid out as rows of 16
-// entries (one row = one half-warp of one step) filled column by column from the entries
-// sorted by bank pair: entries of the same bank pair land in different rows, and a row sees a
-// bank pair ceil(count / rows) times instead of the ~2.6 of a random order.
-// One warp per segment, chunks of kOrderChunk entries staged in shared memory.
+// accumulator: the hardware serves that as two half-warps of 16 lanes, and a half-warp costs
+// as many shared-memory wavefronts as its most-requested 8-byte bank pair (accumulator index
+// mod 16) is asked for.  Entry order inside a segment is free (integer adds commute), so the
+// segment is composed as rows of 16 entries (one row = one half-warp of one step):
+//
+//   1. every bank pair c with l_c entries puts one entry into each of the rows 0 .. l_c - 1
+//      (largest l_c first, rows that are full are skipped): a row then asks for each pair once;
+//   2. what did not fit (pairs with more entries than there are rows) fills the free places of
+//      the later rows, at most one more entry per pair and row at a time.
+//
+//   The segment stays compact (no holes) and costs about max_c l_c wavefronts per access, the
+//   minimum for the given l_c, instead of the ~1.3 x max_c l_c of a column-by-column deal.
+//
+// Hot genes (SPADE_TWO_CHOICE = H > 0, common.cuh): the H genes of a partition with the most
+// stored values after the dense head own a second accumulator in another bank pair; per
+// segment each of their entries is given to A or B so that max_c l_c comes down (greedy on the
+// emptier pair, then moves out of overfull pairs) before the rows are composed.
+// One warp per segment, chunks of kOrderChunk entries staged in shared memory; lane 0 does the
+// serial part (a segment holds ~50 entries).
 // ------------------------------------------------------------------------------------------
 constexpr int kOrderChunk = 512;
-constexpr int kOrderWarps = 8;
+constexpr int kOrderWarps = 5;       // 8.4 KB of scratch per warp
 
-// entries [beg, end) of one segment, chunk by chunk; `buf` / `bins`: this warp's scratch
-__device__ void bank_order_segment(unsigned long long *__restrict__ ent, uint32_t beg, uint32_t end,
-                                   unsigned long long *buf /*kOrderChunk*/, int *bins /*16*/, int lane)
+struct OrderScratch {
+    unsigned long long buf[kOrderChunk];   // the chunk's entries
+    uint16_t idx[kOrderChunk];             // accumulator index an entry adds into (A or B)
+    uint16_t alt[kOrderChunk];             // the other accumulator of a hot gene's entry, 0xffff = none
+    uint16_t by_pair[kOrderChunk];         // entries grouped by bank pair
+    uint16_t pos[kOrderChunk];             // final place of an entry inside the chunk
+    int cnt[16], start[16], fill[16];
+    uint8_t occ[kOrderChunk / 16];
+};
+
+// entries [beg, end) of one segment, chunk by chunk.  hotb: per gene of the partition (index =
+// slot) the B accumulator of a hot gene (Gp + hotb[slot]) or a negative value; null = no hot genes.
+__device__ void order_segment(unsigned long long *__restrict__ ent, uint32_t beg, uint32_t end, int Gp,
+                              const int16_t *__restrict__ hotb, OrderScratch &w, int lane)
 {
     for (uint32_t c0 = beg; c0 < end; c0 += kOrderChunk) {
         const int m = (int)min((uint32_t)kOrderChunk, end - c0);
-        if (m <= 16) break;                                  // a single row: nothing to gain
+        if (m <= 16 && !hotb) break;                         // a single row of distinct genes: nothing to gain
         const int rows = (m + 15) >> 4;
-        const int r = m - 16 * (rows - 1);                   // entries of the last row
-        if (lane < 16) bins[lane] = 0;
-        __syncwarp();
         for (int i = lane; i < m; i += 32) {
             const unsigned long long e = ent[c0 + i];
-            buf[i] = e;
-            atomicAdd(&bins[(int)(e >> kFieldBits) & 15], 1);
+            const int sl = (int)(e >> kFieldBits);
+            w.buf[i] = e;
+            w.idx[i] = (uint16_t)sl;
+            const int hb = hotb ? hotb[sl] : -1;
+            w.alt[i] = hb >= 0 ? (uint16_t)(Gp + hb) : (uint16_t)0xffff;
+        }
+        if (lane < 16) w.cnt[lane] = 0;
+        __syncwarp();
+        if (hotb && lane == 0) {
+            // A or B for the entries of hot genes: fixed entries first, then greedy, then moves
+            const int L = rows;
+            for (int i = 0; i < m; ++i)
+                if (w.alt[i] == 0xffff) ++w.cnt[w.idx[i] & 15];
+            for (int i = 0; i < m; ++i) {
+                if (w.alt[i] == 0xffff) continue;
+                const int a = w.idx[i] & 15, o = w.alt[i] & 15;
+                if (w.cnt[a] <= w.cnt[o]) { ++w.cnt[a]; }
+                else { const uint16_t t = w.idx[i]; w.idx[i] = w.alt[i]; w.alt[i] = t; ++w.cnt[o]; }
+            }
+            for (int pass = 0; pass < 4; ++pass) {
+                bool moved = false;
+                for (int i = 0; i < m; ++i) {
+                    if (w.alt[i] == 0xffff) continue;
+                    const int cur = w.idx[i] & 15, o = w.alt[i] & 15;
+                    if (w.cnt[cur] > L && w.cnt[o] + 1 < w.cnt[cur]) {
+                        const uint16_t t = w.idx[i]; w.idx[i] = w.alt[i]; w.alt[i] = t;
+                        --w.cnt[cur]; ++w.cnt[o];
+                        moved = true;
+                    }
+                }
+                if (!moved) break;
+            }
+        } else if (!hotb) {
+            for (int i = lane; i < m; i += 32) atomicAdd(&w.cnt[w.idx[i] & 15], 1);
         }
         __syncwarp();
-        {   // exclusive scan of the 16 bins
-            int v = lane < 16 ? bins[lane] : 0, inc = v;
+        {   // group the entries by bank pair: exclusive scan of the 16 counts, then a counting sort
+            int v = lane < 16 ? w.cnt[lane] : 0, inc = v;
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            __syncwarp();
-            if (lane < 16) bins[lane] = inc - v;
+            if (lane < 16) { w.start[lane] = inc - v; w.fill[lane] = 0; }
         }
         __syncwarp();
         for (int i = lane; i < m; i += 32) {
-            const unsigned long long e = buf[i];
-            const int j = atomicAdd(&bins[(int)(e >> kFieldBits) & 15], 1);   // rank in bank order
-            int row, col;
-            if (j < r * rows) {
-                col = j / rows;
-                row = j - col * rows;
-            } else {
-                const int j2 = j - r * rows;                 // rows >= 2 here (m > 16, r <= 16)
-                col = r + j2 / (rows - 1);
-                row = j2 % (rows - 1);
-            }
-            ent[c0 + row * 16 + col] = e;
+            const int c = w.idx[i] & 15;
+            w.by_pair[w.start[c] + atomicAdd(&w.fill[c], 1)] = (uint16_t)i;
         }
+        __syncwarp();
+        if (lane == 0) {
+            const int last_cap = m - 16 * (rows - 1);
+            for (int r = 0; r < rows; ++r) w.occ[r] = 0;
+            int order[16];
+            for (int c = 0; c < 16; ++c) order[c] = c;
+            for (int i = 1; i < 16; ++i) {                   // bank pairs by decreasing count
+                const int c = order[i];
+                int j = i - 1;
+                while (j >= 0 && w.cnt[order[j]] < w.cnt[c]) { order[j + 1] = order[j]; --j; }
+                order[j + 1] = c;
+            }
+            for (int q = 0; q < 16; ++q) {                   // 1. one entry per row
+                const int c = order[q];
+                int j = 0;
+                for (int r = 0; r < rows && j < w.cnt[c]; ++r) {
+                    const int cap = r == rows - 1 ? last_cap : 16;
+                    if (w.occ[r] >= cap) continue;
+                    w.pos[w.by_pair[w.start[c] + j]] = (uint16_t)(16 * r + w.occ[r]);
+                    ++w.occ[r];
+                    ++j;
+                }
+                w.fill[c] = j;                               // entries of the pair placed so far
+            }
+            int r = 0;                                       // 2. the rest, one per pair and row at a time
+            bool left = true;
+            while (left) {
+                left = false;
+                for (int q = 0; q < 16; ++q) {
+                    const int c = order[q];
+                    if (w.fill[c] >= w.cnt[c]) continue;
+                    while (r < rows && w.occ[r] >= (r == rows - 1 ? last_cap : 16)) ++r;
+                    if (r >= rows) break;                    // cannot happen: places = entries
+                    w.pos[w.by_pair[w.start[c] + w.fill[c]]] = (uint16_t)(16 * r + w.occ[r]);
+                    ++w.occ[r];
+                    ++w.fill[c];
+                    left = true;
+                }
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32)
+            ent[c0 + w.pos[i]] = ((unsigned long long)w.idx[i] << kFieldBits) | (w.buf[i] & ((1ull << kFieldBits) - 1));
         __syncwarp();
     }
 }
 
 __global__ void __launch_bounds__(kOrderWarps * 32)
-k_bank_order(const uint2 *__restrict__ segs, int64_t nseg, int64_t C, const uint8_t *__restrict__ dense_on,
-             unsigned long long *__restrict__ ent)
+k_order_segments(const uint2 *__restrict__ segs, int64_t nseg, int64_t C, int Gp, int hot,
+                 const int16_t *__restrict__ hotb, const uint8_t *__restrict__ dense_on,
+                 unsigned long long *__restrict__ ent)
 {
-    __shared__ unsigned long long buf[kOrderWarps][kOrderChunk];
-    __shared__ int bins[kOrderWarps][16];
+    __shared__ OrderScratch scratch[kOrderWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t seg = blockIdx.x * (int64_t)kOrderWarps + warp;
     if (seg >= nseg) return;
-    const uint32_t beg = segs[seg].x + (dense_on[seg / C] ? kDenseLanes : 0), end = segs[seg].y;
-    bank_order_segment(ent, beg, end, buf[warp], bins[warp], lane);
-}
-
-// ------------------------------------------------------------------------------------------
-// Two-choice layout (see common.cuh): per segment, pick for every entry accumulator A or B so
-// that no bank pair is asked for more than ceil(n / 16) times (greedy on the emptier of the two
-// banks, then single and double moves out of overfull banks), and store the entries as rows of
-// 16 with COLUMN = BANK PAIR: lane j of a half-warp always touches bank pair j, so the
-// read-modify-write of a row is one conflict-free wavefront.  Cell (row r, bank b) holds the
-// r-th entry of bank b or a hole (zero add into the spare accumulator of bank b).  A segment
-// gets ceil(n / 16) rows, one more when the assignment needs it (the layout reserves it); in the
-// rare case that even that is not enough, or for segments above kOrderChunk entries, the
-// conflict-tolerant order above is used instead.  The kernel rewrites seg[].y (end of the rows).
-// ------------------------------------------------------------------------------------------
-constexpr int kTwoWarps = 6;        // warps per CTA of k_two_choice (7.7 KB of scratch per warp)
-
-__global__ void __launch_bounds__(kTwoWarps * 32)
-k_two_choice(uint2 *__restrict__ segs, const uint32_t *__restrict__ cursor, int64_t nseg, int64_t C, int Gp,
-             const uint8_t *__restrict__ dense_on, unsigned long long *__restrict__ ent)
-{
-    __shared__ unsigned long long buf[kTwoWarps][kOrderChunk];
-    __shared__ int bins[kTwoWarps][16];
-    __shared__ uint8_t bank[kTwoWarps][kOrderChunk];       // chosen bank pair of every entry
-    __shared__ uint8_t other[kTwoWarps][kOrderChunk];      // its alternative
-    __shared__ uint16_t rank_in_bank[kTwoWarps][kOrderChunk];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t seg = blockIdx.x * (int64_t)kTwoWarps + warp;
-    if (seg >= nseg) return;
-    const uint32_t beg = segs[seg].x + (dense_on[seg / C] ? kDenseLanes : 0);
-    const uint32_t end = cursor[seg];                        // one past the last scattered entry
-    const int n = (int)(end - beg);
-    if (n == 0) return;
-    if (n > kOrderChunk) {                                   // very dense cell: conflict-tolerant order, A only
-        bank_order_segment(ent, beg, end, buf[warp], bins[warp], lane);
-        if (lane == 0) segs[seg].y = end;
-        return;
-    }
-    unsigned long long *b = buf[warp];
-    uint8_t *bk = bank[warp], *ot = other[warp];
-    int *load = bins[warp];
-    for (int i = lane; i < n; i += 32) b[i] = ent[beg + i];
-    if (lane < 16) load[lane] = 0;
-    __syncwarp();
-    const int L = (n + 15) >> 4;
-    int rows = 0;
-    if (lane == 0) {
-        for (int i = 0; i < n; ++i) {                        // greedy: the emptier of the two banks
-            const int s = (int)(b[i] >> kFieldBits);
-            const int a = s & 15, o = alt_slot(s) & 15;
-            if (load[a] <= load[o]) { bk[i] = a; ot[i] = o; ++load[a]; }
-            else { bk[i] = o; ot[i] = a; ++load[o]; }
-        }
-        for (int pass = 0; pass < 4; ++pass) {               // moves out of banks above L
-            bool over = false;
-            for (int i = 0; i < n; ++i) {
-                const int cur = bk[i];
-                if (load[cur] <= L) continue;
-                const int o = ot[i];
-                if (load[o] < L) {
-                    bk[i] = o; ot[i] = cur; --load[cur]; ++load[o];
-                    continue;
-                }
-                bool moved = false;                          // make room in o by moving one of its entries on
-                for (int j = 0; j < n && !moved; ++j) {
-                    if (bk[j] != o || load[ot[j]] >= L) continue;
-                    const int o2 = ot[j];
-                    bk[j] = o2; ot[j] = o; ++load[o2];       // j: o -> o2, i: cur -> o (load[o] unchanged)
-                    bk[i] = o; ot[i] = cur; --load[cur];
-                    moved = true;
-                }
-                over |= !moved;
-            }
-            if (!over) break;
-        }
-        int mx = 0;
-        for (int k = 0; k < 16; ++k) { mx = max(mx, load[k]); load[k] = 0; }
-        for (int i = 0; i < n; ++i) rank_in_bank[warp][i] = (uint16_t)load[bk[i]]++;
-        rows = mx;
-    }
-    rows = __shfl_sync(0xffffffffu, rows, 0);
-    __syncwarp();
-    if (rows > L + 1) {                                      // does not fit the reserved rows: keep A, old order
-        bank_order_segment(ent, beg, end, buf[warp], bins[warp], lane);
-        if (lane == 0) segs[seg].y = end;
-        return;
-    }
-    // holes first, then the entries (index rewritten to the chosen accumulator)
-    for (int i = lane; i < rows * 16; i += 32)
-        ent[beg + i] = (unsigned long long)(2 * Gp + (i & 15)) << kFieldBits;
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-        const unsigned long long e = b[i];
-        const int s = (int)(e >> kFieldBits);
-        const int idx = (bk[i] == (s & 15)) ? s : Gp + alt_slot(s);
-        ent[beg + rank_in_bank[warp][i] * 16 + bk[i]] =
-            ((unsigned long long)idx << kFieldBits) | (e & ((1ull << kFieldBits) - 1));
-    }
-    if (lane == 0) segs[seg].y = beg + rows * 16;
+    const int64_t part = seg / C;
+    const uint32_t beg = segs[seg].x + (dense_on[part] ? kDenseLanes : 0), end = segs[seg].y;
+    order_segment(ent, beg, end, Gp, hot > 0 ? hotb + part * Gp : nullptr, scratch[warp], lane);
 }
 
 }  // namespace spade

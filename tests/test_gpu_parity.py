@@ -326,15 +326,16 @@ def test_layout_switches_do_not_change_results(monkeypatch):
     sets = synth.deobs_sets(C, 9, lo=5, hi=1200) + synth.derand_draws(C, 77, 5)
     nc = np.arange(1, C, 13)
     res = {}
-    for dense, order in ((1, 1), (0, 1), (1, 0), (0, 0), (1, "two"), (0, "two")):
+    for dense, order in ((1, 1), (0, 1), (1, 0), (0, 0), (1, "two"), (0, "two"), (1, "hot"), (0, "hot")):
         monkeypatch.setenv("SPADE_DENSE_BLOCKS", str(dense))
-        monkeypatch.setenv("SPADE_BANK_ORDER", "1" if order == "two" else str(order))
-        monkeypatch.setenv("SPADE_TWO_CHOICE", "1" if order == "two" else "0")   # two accumulators per gene
+        monkeypatch.setenv("SPADE_BANK_ORDER", "1" if order in ("two", "hot") else str(order))
+        # a second accumulator for every gene ("two") or for the 64 hottest genes of a partition
+        monkeypatch.setenv("SPADE_TWO_CHOICE", {"two": "1", "hot": "64"}.get(order, "0"))
         with Engine.from_counts(counts) as eng:
             a = eng.run(sets, want_k=True)
             eng.set_background(nc)
             b = eng.run(sets, want_k=True)
-            if order == "two":                              # re-staging and other partition widths
+            if order in ("two", "hot"):                     # re-staging and other partition widths
                 eng.set_background(None)
                 _tables_equal(a, eng.run(sets, want_k=True))
                 eng.set_option("genes_per_part", 96)
