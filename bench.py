@@ -487,6 +487,10 @@ def main():
             return
         import ctypes
         exchange.step(members, offsets, rank, world, sizes_all)       # host member lists: uploaded by the call
+        exchange.drain()                                               # this step's gene block is finished
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        exchange.side.wait_event(ready)
         g0, g1 = exchange.gene_begin, exchange.gene_end
         if g1 > g0:
             for k in TABLES:
@@ -495,12 +499,9 @@ def main():
                                         ctypes.c_void_p(exchange.tables[k].data_ptr()), 8 * exchange.cols,
                                         8 * (g1 - g0), S * world, 1, ctypes.c_void_p(exchange.side.cuda_stream))
                 assert rc == 0
-        done = torch.cuda.Event()
-        done.record(exchange.side)
-        exchange.expanded = done                                       # the copies belong to this step
-        exchange.drain()
-        torch.cuda.current_stream().synchronize()
+        exchange.side.synchronize()
         dist.all_reduce(exchange.flag)                                 # every rank's block is in the shared tables
+        torch.cuda.current_stream().synchronize()
 
     def timed(fn, steps, warmup, ex=exchange):
         def drain():
@@ -585,7 +586,11 @@ def main():
                 "algorithmic_bytes_per_launch": path_bytes, "launch_ms": test_ms,
                 "launches_per_step": len(kernels), "kernels": kernels,
                 "bytes_per_test": path_bytes / (S * G), "gather_bytes_per_launch": gather_bytes,
-                "sets_per_launch": S, "other_kernels_ms_per_step": table_ms}
+                "sets_per_launch": S, "other_kernels_ms_per_step": table_ms,
+                "note": "algorithmic bytes of SURVEY 8-d against the measured HBM copy bandwidth; the cell-major layout "
+                        "(1.1 GB) is re-read by every set and served from L2 (measured DRAM traffic = `traffic`, about a "
+                        "quarter of the algorithmic bytes), so the fraction of k_de_fused can exceed 1: its binding unit is "
+                        "the SM's LSU data pipe (l1tex__throughput 88 % under ncu, profiles/r02_ncu_full_two_phase.json)"}
 
     line = None
     if rank == 0:

@@ -159,14 +159,19 @@ class GeneExchange:
     docstring).  One object per rank and engine; ``max_rows`` = the largest number of sets (over
     ALL ranks) of one step.
 
-    ``step(members, offsets, first_row, row_step, set_sizes)`` is asynchronous: the routed raw
-    launch and a 4-byte NCCL all-reduce ("every rank's words have landed") go on the current
-    stream, the expansion of this rank's gene block on a side stream, so that the test kernel of
-    the next step overlaps it.  Two word buffers are used in turn; the expansion of step i is
-    waited for before this rank enters the all-reduce of step i + 1, which is what allows the
-    peers to overwrite that buffer in step i + 2.  ``drain()`` makes the current stream wait for
-    the last expansion; then ``tables[name][:rows]`` holds ALL sets x the genes
+    ``step(members, offsets, first_row, row_step, set_sizes)`` is asynchronous.  On the current
+    stream: the routed raw launch of this step, then the expansion of the PREVIOUS step's gene block
+    (the two compete for the same SMs, so they are not overlapped).  On a side stream: a 4-byte NCCL
+    all-reduce per step ("every rank's words of this step have landed"), which the expansion of that
+    step waits for one step later - by then it has normally passed, so the ranks do not run in
+    lockstep and a rank may be up to one step behind the others.  Four word buffers are used in
+    turn: the kernel of step i + 1 follows this rank's wait for the all-reduce of step i - 1, which
+    completes only after every rank has launched its kernel of step i - 1, i.e. finished its
+    expansion of step i - 3 - the last reader of the buffer step i + 1 writes into.  ``drain()``
+    finishes the last step; then ``tables[name][:rows]`` holds ALL sets x the genes
     ``[gene_begin, gene_end)`` of this rank, rows in global set order."""
+
+    BUFFERS = 4
 
     def __init__(self, engine, max_rows, tables=("up", "down", "cpm"), want_k=False, rank=None,
                  world_size=None, device=None):
@@ -184,15 +189,16 @@ class GeneExchange:
         self.blocks = gene_blocks(engine.G, engine.genes_per_part, self.world)
         self.gene_begin, self.gene_end = self.blocks[self.rank]
         self.width = max(1, max(b - a for a, b in self.blocks))
-        self.words = PeerBuffers(self.max_rows * self.width * 8, self.rank, self.world, self.device, count=2)
+        self.words = PeerBuffers(self.max_rows * self.width * 8, self.rank, self.world, self.device,
+                                 count=self.BUFFERS)
         dev = torch.device("cuda", self.device)
         cols = max(1, self.gene_end - self.gene_begin)
         self.cols = cols
         self.tables = {n: torch.empty((self.max_rows, cols), dtype=torch.float64, device=dev) for n in tables}
         self.k = torch.empty((self.max_rows, cols), dtype=torch.int32, device=dev) if want_k else None
-        self.side = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev, priority=-1)      # all-reduces (and the bench's table copies)
         self.flag = torch.zeros(1, device=dev)
-        self.expanded = None
+        self.pending = None                            # (buffer, set sizes, rows, all-reduce event) of the last step
         self.steps = 0
         self._dist = dist
 
@@ -201,31 +207,39 @@ class GeneExchange:
 
         rows = len(set_sizes)
         assert rows <= self.max_rows
-        buf = self.steps & 1
+        buf = self.steps % self.BUFFERS
         self.steps += 1
         main = torch.cuda.current_stream(self.device)
         blocks = [(self.words.ptr[buf][q], self.width, a, b) for q, (a, b) in enumerate(self.blocks)]
         if len(offsets) > 1:
             self.engine.run_raw_blocks(members, offsets, blocks, first_row, row_step, stream=main)
-        if self.expanded is not None:
-            main.wait_event(self.expanded)
-        self.flag.zero_()
-        self._dist.all_reduce(self.flag)               # passes once every rank's kernel has finished
+        stored = torch.cuda.Event()
+        stored.record(main)
+        self.side.wait_event(stored)
+        with torch.cuda.stream(self.side):
+            self.flag.zero_()
+            self._dist.all_reduce(self.flag)           # passes once every rank's kernel of this step has finished
         landed = torch.cuda.Event()
-        landed.record(main)
-        self.side.wait_event(landed)
+        landed.record(self.side)
+        self._finish_pending(main)                     # the previous step, behind this step's kernel
+        self.pending = (buf, np.array(set_sizes, dtype=np.int64), rows, landed)
+        self.rows = rows
+
+    def _finish_pending(self, stream):
+        if self.pending is None:
+            return
+        buf, set_sizes, rows, landed = self.pending
+        self.pending = None
+        stream.wait_event(landed)
         if self.gene_end > self.gene_begin and rows:
             self.engine.expand_block(self.words.ptr[buf][self.rank], set_sizes, self.gene_begin,
                                      self.gene_end - self.gene_begin, self.tables, k=self.k,
-                                     raw_row_stride=self.width, row_stride=self.cols, stream=self.side)
-        self.expanded = torch.cuda.Event()
-        self.expanded.record(self.side)
-        self.rows = rows
+                                     raw_row_stride=self.width, row_stride=self.cols, stream=stream)
 
     def drain(self):
+        """Finish the last step on the current stream."""
         import torch
-        if self.expanded is not None:
-            torch.cuda.current_stream(self.device).wait_event(self.expanded)
+        self._finish_pending(torch.cuda.current_stream(self.device))
 
     def close(self):
         import torch
