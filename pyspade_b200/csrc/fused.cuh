@@ -184,7 +184,7 @@ __device__ __forceinline__ void decode_entry(unsigned long long e, uint32_t &slo
 
 // The register accumulators of the dense head join the shared-memory ones, and the second
 // accumulators of the hot genes are added into the first.
-__device__ __forceinline__ void hand_over_dense(const RunArgs &a, unsigned long long *acc,
+__device__ __forceinline__ void collect_accumulators(const RunArgs &a, unsigned long long *acc,
                                                 const unsigned long long (&dacc)[kDenseRegs], bool dense, int lane,
                                                 int p, int64_t g0)
 {
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
             process(A);
         }
     }
-    hand_over_dense(a, acc, dacc, dense, lane, p, g0);
+    collect_accumulators(a, acc, dacc, dense, lane, p, g0);
     if (!kSplit) {
         finish_task<kRawOnly>(a, acc, lane, p, g0, ng, row, N);
     } else {

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, SPADE_TMA_MIN_CTAS) k_de_tma(c
             if (!kBulk) cp_async_commit();
         }
     }
-    hand_over_dense(a, acc, dacc, dense, lane, p, g0);
+    collect_accumulators(a, acc, dacc, dense, lane, p, g0);
     finish_task(a, acc, lane, p, g0, ng, row, N);
 }
 
