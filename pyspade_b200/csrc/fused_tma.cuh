@@ -1,17 +1,21 @@
-// The batched test with TMA-staged segments (sm_100a): same task, layout and results as
-// k_de_fused<false> (fused.cuh), different data movement.  k_de_fused pulls every packed entry
-// through the LSU into registers (ld.global, 8 bytes per lane: the fill and the read-out of the
-// line both pass the L1 data stage); here one elected lane per warp asks the TMA unit for a whole
-// (partition, cell) segment with ONE cp.async.bulk into a private shared-memory ring, completion
-// counted in bytes on an mbarrier, kTmaStages segments in flight per warp.  The lanes then read
-// the entries from shared memory (conflict-free 64-bit reads) and add them into the warp's
-// accumulators as before.  The copies are asynchronous, so the latency of L2 is covered by the
-// ring instead of by resident warps - which is what makes the two-accumulator layout (16 KB per
-// warp, see common.cuh) affordable.
+// EXPERIMENT (SPADE_TMA=1 / 2, off by default: measured slower).
+// The batched test with segments staged through shared memory (sm_100a): same task, layout and
+// results as k_de_fused<false> (fused.cuh), different data movement.  k_de_fused pulls every packed
+// entry through the LSU into registers (ld.global, 8 bytes per lane).  Here a warp keeps a private
+// ring of kTmaStages x kStageEnt entries in shared memory and fills it asynchronously, either with
+// ONE cp.async.bulk per (partition, cell) segment issued by an elected lane to the TMA unit
+// (completion counted in bytes on an mbarrier; k_de_tma<true>) or with 16-byte cp.async copies by
+// all lanes (one commit group per segment; k_de_tma<false>).  The lanes then read the entries from
+// shared memory (conflict-free 64-bit reads) and add them into the warp's accumulators as before.
+// The idea: asynchronous copies cover the latency of L2 with the ring instead of with resident
+// warps, which would make a second accumulator for EVERY gene (16 KB per warp) affordable.
+// Measured per 1 000 draws of 500 cells: TMA 3.55 ms (the ~650-byte copies are bound by the TMA
+// unit's per-copy service time), cp.async 2.96 ms, k_de_fused 2.01 ms (profiles/r02_tma_bulk_sweep.log,
+// profiles/r02_ldgsts_ring_sweep.log).
 //
-// Per warp, in shared memory: accumulators | ring of kTmaStages x kStageEnt entries | 32 segment
-// bounds of the current member group | kTmaStages mbarriers | kTmaStages chunk descriptors.
-// A segment longer than a stage is taken in chunks of kStageEnt entries.
+// Per warp, in shared memory: accumulators | ring | 32 segment bounds of the current member group |
+// kTmaStages mbarriers | kTmaStages chunk descriptors.  A segment longer than a stage is taken in
+// chunks of kStageEnt entries.
 #pragma once
 #include "fused.cuh"
 
