@@ -165,6 +165,8 @@ struct RunArgs {
     int dst_pbegin[kMaxGeneBlocks + 1];
     int64_t raw_row0, raw_row_step;
     int p0, p1;                   // gene partitions of this launch
+    int coop;                     // warps of a CTA that share one (partition, set) task: 1, 2 or 4 (non-split form).
+                                  // Each takes a contiguous part of the member list; the accumulators meet in shared memory.
     int Gp;
     int two;                      // hot genes per partition (common.cuh), 0 = none: a test is finished from A + B
     const int16_t *hot_slot;      // [P * two] slot of the gene whose B accumulator is Gp + b, negative = unused
@@ -209,10 +211,10 @@ __device__ __forceinline__ void collect_accumulators(const RunArgs &a, unsigned 
 // What a warp does with the finished accumulators of its (partition p, set `row`) task: the raw
 // words to the owner of the gene block (routed), the raw words to one table, or the finished tests.
 // kRawOnly: instantiation without the finalize code (raw forms only; fewer registers).
-template <bool kRawOnly = false>
-__device__ __forceinline__ void finish_task(const RunArgs &a, const unsigned long long *acc, int lane, int p,
-                                            int64_t g0, int ng, int64_t row, long long N)
-{
+template <bool kRawOnly = false, int stride = 32>
+__device__ __forceinline__ void finish_task(const RunArgs &a, const unsigned long long *acc, int lane,
+                                            int p, int64_t g0, int ng, int64_t row, long long N)
+{   // `lane` = index of the thread among the `stride` threads that finish this task together
     // the accumulator word of gene j of the partition (count << 48 | sum)
     auto word = [&](int j) -> unsigned long long { return acc[j]; };
     if (a.ndst > 0) {
@@ -222,20 +224,20 @@ __device__ __forceinline__ void finish_task(const RunArgs &a, const unsigned lon
         while (b + 1 < a.ndst && p >= a.dst_pbegin[b + 1]) ++b;
         unsigned long long *dst = a.dst_base[b] + (a.raw_row0 + row * a.raw_row_step) * a.dst_ld[b] +
                                   (g0 - (int64_t)a.dst_pbegin[b] * a.Gp);
-        for (int j = lane; j < ng; j += 32) dst[j] = word(j);
+        for (int j = lane; j < ng; j += stride) dst[j] = word(j);
     } else if (kRawOnly || a.raw) {
         // raw form: the accumulator words leave as they are (8 bytes per test instead of 24-36);
         // whoever receives them finishes the tests with k_expand
-        for (int j = lane; j < ng; j += 32) a.raw[row * a.raw_ld + g0 + j] = word(j);
+        for (int j = lane; j < ng; j += stride) a.raw[row * a.raw_ld + g0 + j] = word(j);
     } else if (!kRawOnly) {
         const double invN = 1.0 / (double)N;
         const double invRest = 1.0 / (double)((long long)a.C - N);
         // kFinBatch genes per lane at a time: their metadata / table loads overlap
-        for (int j0 = lane; j0 < ng; j0 += 32 * kFinBatch) {
+        for (int j0 = lane; j0 < ng; j0 += stride * kFinBatch) {
             FinItem it[kFinBatch];
 #pragma unroll
             for (int u = 0; u < kFinBatch; ++u) {
-                const int j = j0 + 32 * u;
+                const int j = j0 + stride * u;
                 if (j < ng) {
                     const long long v = (long long)word(j);
                     const long long sumfx = (v << 16) >> 16;
@@ -245,14 +247,14 @@ __device__ __forceinline__ void finish_task(const RunArgs &a, const unsigned lon
             }
 #pragma unroll
             for (int u = 0; u < kFinBatch; ++u) {
-                const int j = j0 + 32 * u;
+                const int j = j0 + stride * u;
                 if (j < ng) fin_store(a.fin, row, g0 + j, it[u], N, invN, invRest);
             }
         }
     }
 }
 
-template <bool kSplit, bool kRawOnly = false>
+template <bool kSplit, bool kRawOnly = false, int kCoop = 1>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(const RunArgs a)
 {
     extern __shared__ unsigned long long smem_acc[];
@@ -260,10 +262,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     unsigned long long *acc = smem_acc + (size_t)warp * a.acc_len;
     uint2 *mbuf = reinterpret_cast<uint2 *>(smem_acc + (size_t)kWarpsPerCta * a.acc_len) + warp * 32;
 
+    // Few sets per partition (DEobs: hundreds of regions): `coop` warps of the CTA share a task, so
+    // that the resident warps work on two or three gene partitions instead of seven and the cell-major
+    // layout of those partitions stays in L2 (and a long region is cut into shorter member lists).
+    constexpr int coop = kSplit ? 1 : kCoop;   // (= a.coop)
+    const int part = warp % coop;              // which part of the member list
     const int64_t units = kSplit ? a.nblk : a.S;
-    const int64_t t = blockIdx.x * (int64_t)kWarpsPerCta + warp;
+    const int64_t t = blockIdx.x * (int64_t)(kWarpsPerCta / coop) + warp / coop;
     const int64_t pi = t / units;
-    if (pi >= a.p1 - a.p0) return;
+    if (pi >= a.p1 - a.p0) return;             // (all warps of a task group leave together)
     const int p = a.p0 + (int)pi;
     const int64_t u = t - pi * units;
 
@@ -279,6 +286,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
         mbeg = a.offsets[a.s0 + row];
         N = a.offsets[a.s0 + row + 1] - mbeg;
         cntm = (int)N;
+        if (coop > 1) {
+            const int chunk = (cntm + coop - 1) / coop;
+            const int first = min(cntm, part * chunk);
+            cntm = min(cntm, first + chunk) - first;
+            mbeg += first;
+        }
     }
     const int64_t g0 = (int64_t)p * a.Gp;
     const int ng = (int)min((int64_t)a.Gp, a.fin.G - g0);
@@ -390,7 +403,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SPADE_MIN_CTAS) k_de_fused(
     }
     collect_accumulators(a, acc, dacc, dense, lane, p, g0);
     if (!kSplit) {
-        finish_task<kRawOnly>(a, acc, lane, p, g0, ng, row, N);
+        if (coop > 1) {
+            // the parts meet in the accumulators of the group's first warp (named barrier per group)
+            const int group = warp / coop, gthreads = coop * 32, gtid = part * 32 + lane;
+            unsigned long long *acc0 = smem_acc + (size_t)(group * coop) * a.acc_len;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gthreads) : "memory");
+            for (int j = gtid; j < ng; j += gthreads) {
+                unsigned long long v = acc0[j];
+                for (int w = 1; w < coop; ++w) v += acc0[(size_t)w * a.acc_len + j];
+                acc0[j] = v;
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gthreads) : "memory");
+            finish_task<kRawOnly, coop * 32>(a, acc0, gtid, p, g0, ng, row, N);
+        } else {
+            finish_task<kRawOnly>(a, acc, lane, p, g0, ng, row, N);
+        }
     } else {
         for (int j = lane; j < ng; j += 32) {
             const long long v = (long long)acc[j];

@@ -372,10 +372,12 @@ def test_kernel_forms_do_not_change_results(monkeypatch):
         want = [eng.run(sets, want_k=True) for sets in batches]
         eng.set_background(nc)
         want_nc = [eng.run(sets, want_k=True) for sets in batches]
-    for two_phase, tma, two_choice in ((1, 0, 0), (0, 0, 0), (1, 1, 0), (0, 1, 0), (1, 1, 1), (0, 1, 1)):
+    for two_phase, tma, two_choice, coop in ((1, 0, 0, 1), (0, 0, 0, 1), (1, 1, 0, 0), (0, 1, 0, 0), (1, 2, 1, 0),
+                                             (0, 2, 1, 0), (1, 0, 112, 2), (0, 0, 112, 4), (1, 0, 112, 4)):
         monkeypatch.setenv("SPADE_TWO_PHASE", str(two_phase))
-        monkeypatch.setenv("SPADE_TMA", str(tma))
+        monkeypatch.setenv("SPADE_TMA", str(tma))              # 1 = cp.async.bulk ring, 2 = cp.async ring
         monkeypatch.setenv("SPADE_TWO_CHOICE", str(two_choice))
+        monkeypatch.setenv("SPADE_COOP", str(coop))            # warps per (partition, set) task, 0 = automatic
         with Engine.from_counts(counts) as eng:
             for bg, ref in ((None, want), (nc, want_nc)):
                 eng.set_background(bg)
