@@ -139,7 +139,9 @@ int spade_cpm_values(spade_engine *engine, double *values);
  *                                returns without waiting for the kernels; with host outputs
  *                                it returns when the tables are complete.
  * Sets of any size are accepted (sets above SPADE_OPT_MEMBER_BLOCK cells take a slower
- * split path).
+ * split path).  Device workspace kept by the engine between calls: the per-run tail table and,
+ * for batches of one set size with device outputs, 8 bytes per test of the largest chunk
+ * (at most 2^28 tests = 2 GB) for the accumulator words between the two launches of the test.
  */
 int spade_run(spade_engine *engine, const int32_t *members, int members_location,
               const int64_t *offsets, int64_t S, double *up, double *down, double *fc, double *cpm,
