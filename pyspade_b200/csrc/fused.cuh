@@ -451,9 +451,10 @@ k_finalize_split(const FinCtx f, const unsigned long long *__restrict__ gsum,
 constexpr int kSortMax = 8192;
 constexpr int kSortThreads = 256;
 
+// A duplicated cell index inside the set sits next to its twin after the sort: flagged here (err).
 __global__ void __launch_bounds__(kSortThreads)
 k_sort_members(const int32_t *__restrict__ members, const int64_t *__restrict__ offsets,
-               int32_t *__restrict__ sorted)
+               int32_t *__restrict__ sorted, int *__restrict__ err)
 {
     extern __shared__ int32_t keys[];
     const int64_t beg = offsets[blockIdx.x];
@@ -474,10 +475,13 @@ k_sort_members(const int32_t *__restrict__ members, const int64_t *__restrict__ 
             }
             __syncthreads();
         }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sorted[beg + i] = keys[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        sorted[beg + i] = keys[i];
+        if (i + 1 < n && keys[i] == keys[i + 1]) flag_error(err, 4);
+    }
 }
 
-// After the sort a duplicated cell index inside a set sits next to its twin.
+// The same check after CUB's segmented sort (sets above kSortMax cells).
 __global__ void k_check_duplicates(const int32_t *__restrict__ sorted, const int64_t *__restrict__ offsets,
                                    int64_t S, int64_t total, int *__restrict__ err)
 {

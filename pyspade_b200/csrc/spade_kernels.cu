@@ -944,8 +944,9 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             int m = 32;
             while (m < maxN) m <<= 1;
             k_sort_members<<<(unsigned)S, kSortThreads, m * sizeof(int32_t), st>>>(d_members, engine->offsets.p,
-                                                                                engine->members_sorted.p);
+                                                                                engine->members_sorted.p, engine->d_err);
             CUDA_TRY(cudaGetLastError());
+            engine->launches += 1;
         } else {
             // very large sets: CUB's segmented sort (it synchronises the stream internally)
             size_t tb = 0;
@@ -954,11 +955,12 @@ static int run_impl(spade_engine *engine, const int32_t *members, int members_lo
             CUDA_TRY(engine->sort_temp.reserve(tb));
             CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(engine->sort_temp.p, tb, d_members, engine->members_sorted.p,
                                                         total, S, engine->offsets.p, engine->offsets.p + 1, st));
+            k_check_duplicates<<<grid_for(total, 256), 256, 0, st>>>(engine->members_sorted.p, engine->offsets.p, S, total,
+                                                                     engine->d_err);
+            CUDA_TRY(cudaGetLastError());
+            engine->launches += 2;
         }
         d_members = engine->members_sorted.p;
-        k_check_duplicates<<<grid_for(total, 256), 256, 0, st>>>(d_members, engine->offsets.p, S, total, engine->d_err);
-        CUDA_TRY(cudaGetLastError());
-        engine->launches += 2;
     }
 
     const bool host_out = out_location == SPADE_HOST;
