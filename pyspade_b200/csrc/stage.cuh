@@ -318,6 +318,7 @@ struct OrderScratch {
     uint16_t by_pair[kOrderChunk];         // entries grouped by bank pair
     uint16_t pos[kOrderChunk];             // final place of an entry inside the chunk
     int cnt[16], start[16], fill[16];
+    uint8_t start2[16];                    // place of a bank pair in the order by decreasing count
     uint8_t occ[kOrderChunk / 16];
 };
 
@@ -380,38 +381,50 @@ __device__ void order_segment(unsigned long long *__restrict__ ent, uint32_t beg
         __syncwarp();
         for (int i = lane; i < m; i += 32) {
             const int c = w.idx[i] & 15;
-            w.by_pair[w.start[c] + atomicAdd(&w.fill[c], 1)] = (uint16_t)i;
+            const int k = atomicAdd(&w.fill[c], 1);          // rank of the entry inside its bank pair
+            w.by_pair[w.start[c] + k] = (uint16_t)i;
+            w.pos[i] = (uint16_t)k;
+        }
+        __syncwarp();
+        // 1. one entry per row, in closed form.  With the pairs ordered by decreasing count (q = place of
+        // a pair in that order), row r < rows - 1 holds one entry of every pair with more than r entries -
+        // the first pairs of the order - so the k-th entry of pair q sits at 16 k + q.  The last row has
+        // last_cap places: the first last_cap pairs that reach it get one, what is left goes to step 2.
+        const int last_cap = m - 16 * (rows - 1);
+        int q = 0;                                           // lanes 0..15: place of pair `lane` in the order
+        if (lane < 16) {
+            const int mine = w.cnt[lane];
+            for (int c = 0; c < 16; ++c) {
+                const int other = w.cnt[c];
+                q += (other > mine || (other == mine && c < lane)) ? 1 : 0;
+            }
+            w.start2[lane] = (uint8_t)q;
+            const int placed = min(mine, rows - 1) + ((mine >= rows && q < last_cap) ? 1 : 0);
+            w.fill[lane] = placed;
+        }
+        {   // places taken in row `lane` after step 1
+            int present = 0;
+            if (lane < rows)
+                for (int c = 0; c < 16; ++c) present += w.cnt[c] > lane ? 1 : 0;
+            if (lane < rows) w.occ[lane] = (uint8_t)(lane == rows - 1 ? min(present, last_cap) : present);
+        }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            const int k = w.pos[i], qq = w.start2[w.idx[i] & 15];
+            if (k < rows - 1 || (k == rows - 1 && qq < last_cap)) w.pos[i] = (uint16_t)(16 * k + qq);
         }
         __syncwarp();
         if (lane == 0) {
-            const int last_cap = m - 16 * (rows - 1);
-            for (int r = 0; r < rows; ++r) w.occ[r] = 0;
+            // 2. the rest (pairs with more entries than rows, or that missed the last row) fills the free
+            // places of the rows in order, one more entry per pair and row at a time
             int order[16];
-            for (int c = 0; c < 16; ++c) order[c] = c;
-            for (int i = 1; i < 16; ++i) {                   // bank pairs by decreasing count
-                const int c = order[i];
-                int j = i - 1;
-                while (j >= 0 && w.cnt[order[j]] < w.cnt[c]) { order[j + 1] = order[j]; --j; }
-                order[j + 1] = c;
-            }
-            for (int q = 0; q < 16; ++q) {                   // 1. one entry per row
-                const int c = order[q];
-                int j = 0;
-                for (int r = 0; r < rows && j < w.cnt[c]; ++r) {
-                    const int cap = r == rows - 1 ? last_cap : 16;
-                    if (w.occ[r] >= cap) continue;
-                    w.pos[w.by_pair[w.start[c] + j]] = (uint16_t)(16 * r + w.occ[r]);
-                    ++w.occ[r];
-                    ++j;
-                }
-                w.fill[c] = j;                               // entries of the pair placed so far
-            }
-            int r = 0;                                       // 2. the rest, one per pair and row at a time
+            for (int c = 0; c < 16; ++c) order[w.start2[c]] = c;
+            int r = 0;
             bool left = true;
             while (left) {
                 left = false;
-                for (int q = 0; q < 16; ++q) {
-                    const int c = order[q];
+                for (int o = 0; o < 16; ++o) {
+                    const int c = order[o];
                     if (w.fill[c] >= w.cnt[c]) continue;
                     while (r < rows && w.occ[r] >= (r == rows - 1 ? last_cap : 16)) ++r;
                     if (r >= rows) break;                    // cannot happen: places = entries
