@@ -20,9 +20,12 @@ the hot path over that batch: 33 M (gene, draw) tests per GPU.
             memory, tables delivered to page-locked host memory (H2D + kernels + exchange + D2H
             inside the timed region; N > 1: every rank delivers its gene block over its own PCIe
             link into host tables shared by the node).
-``roofline`` dominant kernel (k_de_fused: member gather + tails + table writes in one launch):
-            algorithmic bytes of SURVEY section 8-d (rho * min(8 N, C/8) + 24 B per test) / its
-            CUDA-event time, against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+``roofline`` the test itself - at N = 1 two launches per step, k_de_fused (member gather into
+            shared-memory accumulators, one 8-byte accumulator word per test out) and k_expand (words
+            -> tails + mean CPM tables): algorithmic bytes of SURVEY section 8-d (rho * min(8 N, C/8) +
+            24 B per test) / their CUDA-event time (live, over the timed region), against the measured
+            HBM copy bandwidth of MEASURED_PEAKS.json; ``kernels`` lists each launch with its own time,
+            bytes and fraction, ``traffic`` the DRAM bytes ncu measured for the step.
 ``cpu_baseline`` the CPU implementation of the path on a bounded sample of the same workload, all
             host cores: the UNMODIFIED reference (``oracle/_ref``, kind "reference") when
             ``build()`` could stage it next to the oracle, else the oracle's per-gene port
